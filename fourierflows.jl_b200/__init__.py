@@ -1,0 +1,23 @@
+"""fourierflows.jl_b200 -- B200-native drop-in for the pseudospectral time-stepping hot path of FourierFlows.jl.
+
+Host-side mirror of the reference API (`OneDGrid/TwoDGrid/ThreeDGrid(dev; nx, Lx, ...)`, `Problem(eqn, stepper, dt, grid)`,
+`stepforward!`/`step_until!`, `dealias!`, `Diagnostic`, user `calcN!`/`L`) over the C ABI of `libfourierflows_b200.so`
+(include/fourierflows_b200.h).  Python + ctypes stands in for Julia + `ccall` (no Julia toolchain in this image; the
+Julia wrapper is `julia/FourierFlowsB200.jl`).  Julia's `f!` is spelled `f` here.
+
+The directory name contains a dot, so import it through the `fourierflows_jl_b200` alias module at the repo root.
+"""
+from . import _lib
+from ._lib import DomainError, FFBError, have_device, launch_count
+from .array import CPU, GPU, DevArray, cxtype, device_array, devzeros, fltype, zeros
+from .domains import (OneDGrid, Plan, ThreeDGrid, TwoDGrid, dealias, getaliasedwavenumbers, gridpoints, ldiv_,
+                      makefilter, mul_)
+from .problem import Clock, EmptyParams, EmptyVars, Equation, Problem
+from .timesteppers import (STEPPERS, TimeStepper, getetdcoeffs_and_expLs, isexplicit, step_until, stepforward)
+from .diagnostics import Diagnostic, increment
+from .utils import axpby, mul_real, parsevalsum, parsevalsum2, spectral_mul
+from . import diffusion as Diffusion
+from .equations import Burgers3D, TwoDNavierStokes
+from .cproblem import CProblem
+
+__all__ = [n for n in dir() if not n.startswith("_")]

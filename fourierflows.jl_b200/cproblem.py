@@ -1,0 +1,94 @@
+"""C-driven problems (`ffb_problem_*`): the whole `stepforward!` loop, including the built-in `calcN!` of the benchmark
+equations, runs inside libfourierflows_b200.so with no host language in the loop (SURVEY 8b, B3 form ii)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from .array import DevArray, cxtype, ffb_dtype
+
+_STEPPER = {"ForwardEuler": L.FFB_FORWARD_EULER, "RK4": L.FFB_RK4, "LSRK54": L.FFB_LSRK54, "ETDRK4": L.FFB_ETDRK4, "AB3": L.FFB_AB3}
+_CALCN = {"zero": L.FFB_CALCN_ZERO, "diffusion": L.FFB_CALCN_DIFFUSION, "vorticity2d": L.FFB_CALCN_VORTICITY2D,
+          "burgers3d": L.FFB_CALCN_BURGERS3D, "callback": L.FFB_CALCN_CALLBACK}
+
+
+class CProblem:
+    def __init__(self, n, Lext, stepper="ETDRK4", dt=1e-3, calcN="vorticity2d", nu=0.0, T=np.float64, aliased_fraction=1 / 3,
+                 coef_dtype=None, kappa: DevArray = None, scalar_zero_L=False, callback=None, filter_kwargs=None, fused=0):
+        n = tuple(int(v) for v in (n if isinstance(n, (tuple, list)) else (n,)))
+        Lext = tuple(float(v) for v in (Lext if isinstance(Lext, (tuple, list)) else (Lext,) * len(n)))
+        self.T = np.dtype(T)
+        self.n = n
+        self.nkr = n[0] // 2 + 1
+        self.spectral_shape = (self.nkr,) + n[1:]
+        cfg = L.ffb_problem_config()
+        cfg.ndim = len(n)
+        cfg.n = (C.c_int64 * 3)(*n, *([1] * (3 - len(n))))
+        cfg.L = (C.c_double * 3)(*Lext, *([1.0] * (3 - len(n))))
+        cfg.dtype = ffb_dtype(self.T)
+        cfg.aliased_fraction = float(aliased_fraction)
+        filtered = stepper.startswith("Filtered")
+        cfg.stepper = _STEPPER[stepper[len("Filtered"):] if filtered else stepper]
+        cfg.filtered = 1 if filtered else 0
+        fk = filter_kwargs or {}
+        if fk:
+            cfg.filter_order, cfg.filter_innerK = float(fk.get("order", 4)), float(fk.get("innerK", 2 / 3))
+            cfg.filter_outerK, cfg.filter_tol = float(fk.get("outerK", 1)), float(fk.get("tol", 1e-15))
+        cfg.dt = float(dt)
+        cfg.calcN = _CALCN[calcN]
+        self._cb = L.CALCN_FN(callback) if callback is not None else L.CALCN_FN()
+        cfg.callback = self._cb
+        cfg.user = None
+        cfg.nu = float(nu)
+        cfg.scalar_zero_L = 1 if scalar_zero_L else 0
+        self._kappa = kappa
+        cfg.kappa = kappa.ptr if kappa is not None else None
+        cfg.coef_dtype = ffb_dtype(np.float64 if coef_dtype is None else coef_dtype)
+        cfg.fused = int(fused)
+        h = C.c_void_p()
+        L.call("ffb_problem_create", C.byref(h), C.byref(cfg))
+        self._h = h
+        p, cnt = C.c_void_p(), C.c_int64()
+        L.call("ffb_problem_sol", self._h, C.byref(p), C.byref(cnt))
+        self.sol = DevArray(self.spectral_shape, cxtype(self.T), ptr=p.value, owner=self)
+
+    @property
+    def clock(self):
+        t, step, dt = C.c_double(), C.c_int64(), C.c_double()
+        L.call("ffb_problem_clock", self._h, C.byref(t), C.byref(step), C.byref(dt))
+        return t.value, step.value, dt.value
+
+    def device_bytes(self):
+        b = C.c_size_t()
+        L.call("ffb_problem_bytes", self._h, C.byref(b))
+        return b.value
+
+    def set_physical(self, field):
+        f = np.asfortranarray(field, dtype=self.T)
+        assert f.shape == self.n
+        L.call("ffb_problem_set_physical", self._h, f.ctypes.data)
+        L.call("ffb_sync")
+
+    def get_physical(self):
+        out = np.empty(self.n, dtype=self.T, order="F")
+        L.call("ffb_problem_get_physical", self._h, out.ctypes.data)
+        return out
+
+    def stepforward(self, nsteps=1):
+        L.call("ffb_step", self._h, int(nsteps))
+
+    def step_until(self, stop_time):
+        L.call("ffb_step_until", self._h, float(stop_time))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            L.load().ffb_problem_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

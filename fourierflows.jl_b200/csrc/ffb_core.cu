@@ -1,0 +1,172 @@
+// Runtime plumbing of libfourierflows_b200: error state, device memory, stream (the B1 seam of SURVEY 8b:
+// `zeros(GPU(), T, dims)` src/utils.jl:80, `device_array(GPU())` src/utils.jl:330, upload src/domains.jl:77,
+// download `Array(x)` src/output.jl:79).
+#include <atomic>
+#include <cstring>
+#include <mutex>
+#include "ffb_common.cuh"
+
+namespace ffb {
+
+static thread_local char g_err[512] = "";
+static cudaStream_t g_stream = nullptr;
+static bool g_stream_owned = false;
+static std::mutex g_mu;
+static std::atomic<uint64_t> g_launches{0};
+static int g_num_sms = 0, g_smem_optin = 0;
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+cudaStream_t current_stream() {
+  if (!g_stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_stream) {
+      if (cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking) != cudaSuccess) g_stream = nullptr;
+      else g_stream_owned = true;
+    }
+  }
+  return g_stream;
+}
+
+static void query_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return;
+  cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&g_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+}
+int num_sms() { if (!g_num_sms) query_device(); return g_num_sms ? g_num_sms : 148; }
+int max_smem_optin() { if (!g_smem_optin) query_device(); return g_smem_optin ? g_smem_optin : 227 * 1024; }
+
+}  // namespace ffb
+
+using namespace ffb;
+
+extern "C" {
+
+const char* ffb_last_error(void) { return g_err; }
+int ffb_version(void) { return 100; }
+
+int ffb_device_count(int* n) {
+  FFB_REQUIRE(n, FFB_EINVAL, "n is NULL");
+  int c = 0;
+  cudaError_t e = cudaGetDeviceCount(&c);
+  if (e != cudaSuccess) { *n = 0; return set_error(FFB_ECUDA, "no CUDA device: %s", cudaGetErrorString(e)); }
+  *n = c;
+  return FFB_OK;
+}
+
+int ffb_set_device(int dev) {
+  FFB_CUDA(cudaSetDevice(dev));
+  g_num_sms = 0; g_smem_optin = 0;
+  return FFB_OK;
+}
+
+int ffb_set_stream(void* s) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_stream_owned && g_stream) { cudaStreamSynchronize(g_stream); cudaStreamDestroy(g_stream); }
+  g_stream = reinterpret_cast<cudaStream_t>(s);
+  g_stream_owned = false;
+  if (!s) {
+    if (cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking) != cudaSuccess)
+      return set_error(FFB_ECUDA, "cudaStreamCreate failed");
+    g_stream_owned = true;
+  }
+  return FFB_OK;
+}
+
+int ffb_get_stream(void** s) {
+  FFB_REQUIRE(s, FFB_EINVAL, "s is NULL");
+  *s = current_stream();
+  FFB_REQUIRE(*s, FFB_ECUDA, "no CUDA stream (no device?)");
+  return FFB_OK;
+}
+
+int ffb_sync(void) {
+  cudaStream_t st = current_stream();
+  FFB_REQUIRE(st, FFB_ECUDA, "no CUDA stream (no device?)");
+  FFB_CUDA(cudaStreamSynchronize(st));
+  return FFB_OK;
+}
+
+int ffb_launch_count(uint64_t* n) {
+  FFB_REQUIRE(n, FFB_EINVAL, "n is NULL");
+  *n = g_launches.load();
+  return FFB_OK;
+}
+
+int ffb_malloc(void** p, size_t bytes) {
+  FFB_REQUIRE(p, FFB_EINVAL, "p is NULL");
+  *p = nullptr;
+  if (bytes == 0) bytes = 16;
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); return set_error(FFB_ENOMEM, "cudaMalloc(%zu bytes) out of memory", bytes); }
+  if (e != cudaSuccess) return set_error(FFB_ECUDA, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+  return FFB_OK;
+}
+
+int ffb_free(void* p) {
+  if (!p) return FFB_OK;
+  // thread-safe (Julia finalizers run on arbitrary threads); cudaFree synchronises the device
+  FFB_CUDA(cudaFree(p));
+  return FFB_OK;
+}
+
+int ffb_memset_zero(void* p, size_t bytes) {
+  if (!bytes) return FFB_OK;
+  FFB_REQUIRE(p, FFB_EINVAL, "p is NULL");
+  FFB_CUDA(cudaMemsetAsync(p, 0, bytes, current_stream()));
+  return FFB_OK;
+}
+
+int ffb_h2d(void* dst, const void* src, size_t bytes) {
+  if (!bytes) return FFB_OK;
+  FFB_REQUIRE(dst && src, FFB_EINVAL, "NULL pointer");
+  FFB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, current_stream()));
+  // pageable sources are staged synchronously by the runtime; pinned ones return immediately
+  return FFB_OK;
+}
+
+int ffb_d2h(void* dst, const void* src, size_t bytes) {
+  if (!bytes) return FFB_OK;
+  FFB_REQUIRE(dst && src, FFB_EINVAL, "NULL pointer");
+  FFB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, current_stream()));
+  FFB_CUDA(cudaStreamSynchronize(current_stream()));
+  return FFB_OK;
+}
+
+int ffb_d2d(void* dst, const void* src, size_t bytes) {
+  if (!bytes) return FFB_OK;
+  FFB_REQUIRE(dst && src, FFB_EINVAL, "NULL pointer");
+  FFB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, current_stream()));
+  return FFB_OK;
+}
+
+int ffb_host_alloc_pinned(void** p, size_t bytes) {
+  FFB_REQUIRE(p, FFB_EINVAL, "p is NULL");
+  FFB_CUDA(cudaMallocHost(p, bytes ? bytes : 16));
+  return FFB_OK;
+}
+
+int ffb_host_free_pinned(void* p) {
+  if (!p) return FFB_OK;
+  FFB_CUDA(cudaFreeHost(p));
+  return FFB_OK;
+}
+
+int ffb_mem_info(size_t* free_b, size_t* total_b) {
+  size_t f = 0, t = 0;
+  FFB_CUDA(cudaMemGetInfo(&f, &t));
+  if (free_b) *free_b = f;
+  if (total_b) *total_b = t;
+  return FFB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,375 @@
+// FFT plans: the B2 seam of SURVEY 8b.  Replaces `plan_flows_fft` / `plan_flows_rfft` (src/domains.jl:2-5) and the
+// `mul!` / `ldiv!` executions on `grid.rfftplan` / `grid.fftplan` (src/diffusion.jl:137,139,154,155,171).
+// A d-dimensional transform is one 1-D pass per dimension (P + (2d-1) S bytes of HBM traffic for r2c / c2r).
+#include <cmath>
+#include <map>
+#include <string>
+#include <vector>
+#include "fft_generic.cuh"
+#include "fft_pow2.cuh"
+#include "fft_pow2_dispatch.h"
+
+namespace ffb {
+
+template <typename T>
+static int upload(std::vector<cx<T>>& host, cx<T>** dev) {
+  void* p = nullptr;
+  int rc = ffb_malloc(&p, host.size() * sizeof(cx<T>));
+  if (rc) return rc;
+  cudaError_t e = cudaMemcpy(p, host.data(), host.size() * sizeof(cx<T>), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { cudaFree(p); return set_error(FFB_ECUDA, "twiddle upload: %s", cudaGetErrorString(e)); }
+  *dev = reinterpret_cast<cx<T>*>(p);
+  return FFB_OK;
+}
+
+// exp(-2*pi*i*q/M) evaluated in long double with octant reduction, rounded once to T
+template <typename T>
+static cx<T> unit_root(long long q, long long M) {
+  q %= M;
+  const long double pi = 3.14159265358979323846264338327950288L;
+  // reduce to first octant for accuracy
+  long long q8 = q * 8;
+  int oct = (int)(q8 / M);
+  long double c, s;
+  long long rem = q8 - (long long)oct * M;  // angle = 2*pi*(oct*M + rem)/(8M)
+  long double th = 2.0L * pi * (long double)rem / (8.0L * (long double)M);  // in [0, pi/4)
+  long double c0 = cosl(th), s0 = sinl(th);
+  const long double h = 0.70710678118654752440084436210485L;
+  switch (oct & 7) {
+    case 0: c = c0; s = s0; break;
+    case 1: c = h * (c0 - s0); s = h * (c0 + s0); break;
+    case 2: c = -s0; s = c0; break;
+    case 3: c = -h * (c0 + s0); s = h * (c0 - s0); break;
+    case 4: c = -c0; s = -s0; break;
+    case 5: c = -h * (c0 - s0); s = -h * (c0 + s0); break;
+    case 6: c = s0; s = -c0; break;
+    default: c = h * (c0 + s0); s = -h * (c0 - s0); break;
+  }
+  return mk<T>((T)c, (T)(-s));
+}
+
+template <typename T>
+struct DimTables {
+  int N = 0;             // complex transform length
+  bool pow2 = false;     // register-resident kernel available
+  cx<T>* tw = nullptr;   // pow2 per-pass twiddles
+  cx<T>* wN = nullptr;   // generic: exp(-2 pi i q / N), q < N
+  cx<T>* twr = nullptr;  // split step: exp(-i pi k / N), k <= N (dim 0 of R2C plans only)
+};
+
+}  // namespace ffb
+
+using namespace ffb;
+
+struct ffb_plan {
+  int ndim, dtype, kind, nbatch, flags;
+  long long n[3];     // physical sizes
+  long long nc[3];    // complex array extents (nc[0] = n0/2+1 for R2C)
+  void* tables[3];    // DimTables<T>*
+  void* ws[3];        // scratch, allocated on first use
+  size_t ws_bytes;    // size of each scratch array
+  std::string desc;
+};
+
+namespace ffb {
+
+template <typename T>
+static int build_tables(ffb_plan* pl) {
+  for (int d = 0; d < pl->ndim; ++d) {
+    auto* tb = new DimTables<T>();
+    pl->tables[d] = tb;
+    const bool split = (pl->kind == FFB_R2C && d == 0);
+    const int N = (int)(split ? pl->n[0] / 2 : pl->n[d]);
+    tb->N = N;
+    int rad[8];
+    const int np = pow2_radices(N, rad);
+    tb->pow2 = !(pl->flags & FFB_PLAN_FORCE_GENERIC) && is_pow2((uint64_t)N) && N >= 2 && N <= pow2_max_n(sizeof(T)) && np > 0;
+    if (tb->pow2) {
+      std::vector<cx<T>> h;
+      int Ns = 1;
+      for (int i = 0; i < np; ++i) {
+        const int r = rad[i];
+        if (Ns > 1)
+          for (int k = 1; k < r; ++k)
+            for (int a = 0; a < Ns; ++a) h.push_back(unit_root<T>((long long)a * k, (long long)Ns * r));
+        Ns *= r;
+      }
+      if (h.empty()) h.push_back(mk<T>(1, 0));
+      int rc = upload(h, &tb->tw);
+      if (rc) return rc;
+    } else {
+      std::vector<cx<T>> h((size_t)std::max(N, 1));
+      for (int q = 0; q < N; ++q) h[q] = unit_root<T>(q, N);
+      if (N == 0) h[0] = mk<T>(1, 0);
+      int rc = upload(h, &tb->wN);
+      if (rc) return rc;
+    }
+    if (split) {
+      std::vector<cx<T>> h((size_t)N + 1);
+      for (int k = 0; k <= N; ++k) h[k] = unit_root<T>(k, 2ll * N);
+      int rc = upload(h, &tb->twr);
+      if (rc) return rc;
+    }
+    char buf[96];
+    snprintf(buf, sizeof(buf), "dim%d:N=%d:%s ", d, N, tb->pow2 ? "pow2-register-stockham" : "generic-mixed-radix");
+    pl->desc += buf;
+  }
+  return FFB_OK;
+}
+
+template <typename T>
+static void free_tables(ffb_plan* pl) {
+  for (int d = 0; d < pl->ndim; ++d) {
+    auto* tb = reinterpret_cast<DimTables<T>*>(pl->tables[d]);
+    if (!tb) continue;
+    cudaFree(tb->tw); cudaFree(tb->wN); cudaFree(tb->twr);
+    delete tb;
+  }
+}
+
+static int ensure_ws(ffb_plan* pl, int count) {
+  for (int i = 0; i < count; ++i)
+    if (!pl->ws[i]) {
+      int rc = ffb_malloc(&pl->ws[i], pl->ws_bytes);
+      if (rc) return rc;
+    }
+  return FFB_OK;
+}
+
+template <typename T>
+static int call_pow2(int N, int mode, int dir, const Pow2Params<T>& p, int gx, int gy, int threads, size_t smem, cudaStream_t st) {
+  int rc;
+  if constexpr (sizeof(T) == 8) {
+    if ((rc = pow2_launch_double_g0(N, mode, dir, &p, gx, gy, threads, smem, st)) != 1) return rc;
+    if ((rc = pow2_launch_double_g1(N, mode, dir, &p, gx, gy, threads, smem, st)) != 1) return rc;
+    if ((rc = pow2_launch_double_g2(N, mode, dir, &p, gx, gy, threads, smem, st)) != 1) return rc;
+    if ((rc = pow2_launch_double_g3(N, mode, dir, &p, gx, gy, threads, smem, st)) != 1) return rc;
+  } else {
+    if ((rc = pow2_launch_float_g0(N, mode, dir, &p, gx, gy, threads, smem, st)) != 1) return rc;
+    if ((rc = pow2_launch_float_g1(N, mode, dir, &p, gx, gy, threads, smem, st)) != 1) return rc;
+    if ((rc = pow2_launch_float_g2(N, mode, dir, &p, gx, gy, threads, smem, st)) != 1) return rc;
+    if ((rc = pow2_launch_float_g3(N, mode, dir, &p, gx, gy, threads, smem, st)) != 1) return rc;
+  }
+  return set_error(FFB_EUNSUPPORTED, "no register-resident FFT kernel for N=%d", N);
+}
+
+// Lines-per-CTA choice.  ROWS: enough lines for >= 256 threads.  COLS: as many adjacent columns as the thread and
+// shared-memory budgets allow, so each HBM access is W*sizeof(complex) wide (>= 128 B wherever it fits).
+template <typename T>
+static int choose_w(int N, int mode, long long nlines) {
+  const int R = pow2_points_per_thread(N);
+  const int Tn = N / R;
+  const int maxT = pow2_max_threads(sizeof(T));
+  const size_t smem_cap = (size_t)max_smem_optin() - 1024;
+  int W = 1;
+  if (mode == C2C_COLS) {
+    const int want = (int)(256 / sizeof(cx<T>));  // 256-byte wide tiles
+    while (W * 2 <= want && Tn * W * 2 <= maxT && pow2_smem_bytes<T>(N, W * 2, mode) <= smem_cap) W *= 2;
+    while (Tn * W < 128 && Tn * W * 2 <= maxT && pow2_smem_bytes<T>(N, W * 2, mode) <= smem_cap) W *= 2;
+  } else {
+    while (Tn * W < 256 && Tn * W * 2 <= maxT && pow2_smem_bytes<T>(N, W * 2, mode) <= smem_cap) W *= 2;
+  }
+  while (W > 1 && W / 2 >= nlines) W /= 2;
+  return W;
+}
+
+// One register-resident pass over `nouter` outer blocks (gridDim.y chunks of <= 65535).
+template <typename T>
+static int pow2_pass(int N, int mode, int dir, const void* in, void* out, long long in_es, long long in_ls, long long in_os,
+                     long long out_es, long long out_ls, long long out_os, long long nlines, long long nouter, T scale,
+                     const DimTables<T>* tb, cudaStream_t st) {
+  Pow2Params<T> p;
+  p.in_es = in_es; p.in_ls = in_ls; p.in_os = in_os;
+  p.out_es = out_es; p.out_ls = out_ls; p.out_os = out_os;
+  p.nlines = nlines;
+  p.W = choose_w<T>(N, mode, nlines);
+  p.scale = scale;
+  p.tw = tb->tw;
+  p.twr = tb->twr;
+  const int R = pow2_points_per_thread(N);
+  const int threads = (N / R) * p.W;
+  const size_t smem = pow2_smem_bytes<T>(N, p.W, mode);
+  const long long gx = (nlines + p.W - 1) / p.W;
+  FFB_REQUIRE(gx < (1ll << 31), FFB_EUNSUPPORTED, "too many lines for one launch");
+  for (long long o0 = 0; o0 < nouter; o0 += 65535) {
+    const long long cnt = std::min<long long>(65535, nouter - o0);
+    p.in = reinterpret_cast<const cx<T>*>(in) + o0 * in_os;
+    p.out = reinterpret_cast<cx<T>*>(out) + o0 * out_os;
+    int rc = call_pow2<T>(N, mode, dir, p, (int)gx, (int)cnt, threads, smem, st);
+    if (rc) return rc;
+  }
+  return FFB_OK;
+}
+
+// c2c pass along dimension d of a dense complex array with extents e[0..2] x nb (x fastest).
+template <typename T>
+static int c2c_dim(ffb_plan* pl, int d, const long long e[3], long long nb, const cx<T>* src, cx<T>* dst, int dir, T scale,
+                   cudaStream_t st) {
+  auto* tb = reinterpret_cast<DimTables<T>*>(pl->tables[d]);
+  const int N = tb->N;
+  long long inner = 1, outer = nb;
+  for (int i = 0; i < d; ++i) inner *= e[i];
+  for (int i = d + 1; i < 3; ++i) outer *= e[i];
+  if (tb->pow2) {
+    if (d == 0)
+      return pow2_pass<T>(N, C2C_ROWS, dir, src, dst, 1, N, 0, 1, N, 0, outer, 1, scale, tb, st);
+    return pow2_pass<T>(N, C2C_COLS, dir, src, dst, inner, 1, inner * N, inner, 1, inner * N, inner, outer, scale, tb, st);
+  }
+  int rc = ensure_ws(pl, 2);
+  if (rc) return rc;
+  return generic_fft_axis<T>(src, dst, reinterpret_cast<cx<T>*>(pl->ws[0]), reinterpret_cast<cx<T>*>(pl->ws[1]), inner, N, outer,
+                             dir, scale, tb->wN, st);
+}
+
+template <typename T>
+static int exec(ffb_plan* pl, const void* in, void* out, int dir) {
+  cudaStream_t st = current_stream();
+  FFB_REQUIRE(st, FFB_ECUDA, "no CUDA stream (no device?)");
+  const int nd = pl->ndim;
+  const long long nb = pl->nbatch;
+  long long e[3] = {pl->nc[0], pl->nc[1], pl->nc[2]};
+  long double tot = 1;
+  for (int d = 0; d < nd; ++d) tot *= (long double)pl->n[d];
+  const T inv = (T)(1.0L / tot);
+
+  if (pl->kind == FFB_C2C) {
+    const cx<T>* src = reinterpret_cast<const cx<T>*>(in);
+    cx<T>* dst = reinterpret_cast<cx<T>*>(out);
+    for (int d = 0; d < nd; ++d) {
+      const T sc = (dir > 0 && d == nd - 1) ? inv : T(1);
+      int rc = c2c_dim<T>(pl, d, e, nb, d == 0 ? src : dst, dst, dir, sc, st);
+      if (rc) return rc;
+    }
+    return FFB_OK;
+  }
+
+  // ---------------- R2C plans ----------------
+  auto* tb0 = reinterpret_cast<DimTables<T>*>(pl->tables[0]);
+  const int N0 = tb0->N;               // nx/2
+  const long long nkr = pl->nc[0];     // nx/2 + 1
+  long long rows = nb;
+  for (int d = 1; d < nd; ++d) rows *= pl->n[d];
+  if (dir < 0) {
+    // forward: x (r2c) into `out`, then y, z in place on `out`
+    cx<T>* dst = reinterpret_cast<cx<T>*>(out);
+    if (tb0->pow2) {
+      int rc = pow2_pass<T>(N0, R2C_ROWS, -1, in, dst, 1, N0, 0, 1, nkr, 0, rows, 1, T(1), tb0, st);
+      if (rc) return rc;
+    } else {
+      int rc = ensure_ws(pl, 3);
+      if (rc) return rc;
+      cx<T>* z = reinterpret_cast<cx<T>*>(pl->ws[2]);
+      rc = generic_fft_axis<T>(reinterpret_cast<const cx<T>*>(in), z, reinterpret_cast<cx<T>*>(pl->ws[0]),
+                               reinterpret_cast<cx<T>*>(pl->ws[1]), 1, N0, rows, -1, T(1), tb0->wN, st);
+      if (rc) return rc;
+      const long long total = rows * (N0 + 1);
+      generic_r2c_post_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(z, dst, N0, rows, tb0->twr);
+      count_launch();
+      FFB_CHECK_LAUNCH();
+    }
+    for (int d = 1; d < nd; ++d) {
+      int rc = c2c_dim<T>(pl, d, e, nb, dst, dst, -1, T(1), st);
+      if (rc) return rc;
+    }
+    return FFB_OK;
+  }
+  // inverse: z, y on a scratch copy of the spectrum (input preserved), then x (c2r) into `out`
+  const cx<T>* spec = reinterpret_cast<const cx<T>*>(in);
+  if (nd > 1) {
+    int rc = ensure_ws(pl, tb0->pow2 ? 1 : 3);
+    if (rc) return rc;
+    // scratch index 2 (generic) or 0 (pow2-only plans) holds the partially transformed spectrum
+    cx<T>* w = reinterpret_cast<cx<T>*>(pl->ws[tb0->pow2 ? 0 : 2]);
+    bool all_pow2 = true;
+    for (int d = 1; d < nd; ++d) all_pow2 = all_pow2 && reinterpret_cast<DimTables<T>*>(pl->tables[d])->pow2;
+    if (!all_pow2 && tb0->pow2) {  // generic y/z passes need ws[0], ws[1] as their own scratch
+      rc = ensure_ws(pl, 3);
+      if (rc) return rc;
+      w = reinterpret_cast<cx<T>*>(pl->ws[2]);
+    }
+    for (int d = nd - 1; d >= 1; --d) {
+      rc = c2c_dim<T>(pl, d, e, nb, d == nd - 1 ? spec : w, w, +1, T(1), st);
+      if (rc) return rc;
+    }
+    spec = w;
+  }
+  if (tb0->pow2) return pow2_pass<T>(N0, C2R_ROWS, +1, spec, out, 1, nkr, 0, 1, N0, 0, rows, 1, inv, tb0, st);
+  int rc = ensure_ws(pl, 3);
+  if (rc) return rc;
+  // generic x: pre-process into ws[2]... but ws[2] may hold `spec`; use ws[0] for Z and route the axis scratch via ws[1]/out
+  cx<T>* z = reinterpret_cast<cx<T>*>(pl->ws[0]);
+  const long long total = rows * N0;
+  generic_c2r_pre_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(spec, z, N0, rows, tb0->twr);
+  count_launch();
+  FFB_CHECK_LAUNCH();
+  // ws[2] is free again once the pre-process has consumed `spec` (stream ordered)
+  cx<T>* tA = reinterpret_cast<cx<T>*>(pl->ws[1]);
+  cx<T>* tB = reinterpret_cast<cx<T>*>(pl->ws[2]);
+  return generic_fft_axis<T>(z, reinterpret_cast<cx<T>*>(out), tA, tB, 1, N0, rows, +1, inv, tb0->wN, st);
+}
+
+}  // namespace ffb
+
+extern "C" {
+
+int ffb_plan_create(ffb_plan** out, int ndim, const int64_t* n, int dtype, int kind, int nbatch, int flags) {
+  FFB_REQUIRE(out && n, FFB_EINVAL, "NULL argument");
+  *out = nullptr;
+  FFB_REQUIRE(ndim >= 1 && ndim <= 3, FFB_EINVAL, "ndim must be 1, 2 or 3 (got %d)", ndim);
+  FFB_REQUIRE(dtype == FFB_F32 || dtype == FFB_F64, FFB_EINVAL, "bad dtype %d", dtype);
+  FFB_REQUIRE(kind == FFB_R2C || kind == FFB_C2C, FFB_EINVAL, "bad kind %d", kind);
+  FFB_REQUIRE(nbatch >= 1, FFB_EINVAL, "nbatch must be >= 1");
+  for (int d = 0; d < ndim; ++d) {
+    FFB_REQUIRE(n[d] >= 2, FFB_EINVAL, "n[%d] = %lld too small", d, (long long)n[d]);
+    FFB_REQUIRE(n[d] < (1ll << 30), FFB_EUNSUPPORTED, "n[%d] = %lld too large", d, (long long)n[d]);
+    // grids require even sizes in every dimension: DomainError, src/domains.jl:66,179,316
+    if (n[d] % 2 != 0) return set_error(FFB_EDOMAIN, "n[%d] = %lld must be even", d, (long long)n[d]);
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return set_error(FFB_ECUDA, "no CUDA device"); }
+  auto* pl = new ffb_plan();
+  pl->ndim = ndim; pl->dtype = dtype; pl->kind = kind; pl->nbatch = nbatch; pl->flags = flags;
+  for (int d = 0; d < 3; ++d) { pl->n[d] = d < ndim ? n[d] : 1; pl->nc[d] = pl->n[d]; pl->tables[d] = nullptr; pl->ws[d] = nullptr; }
+  if (kind == FFB_R2C) pl->nc[0] = pl->n[0] / 2 + 1;
+  pl->ws_bytes = (size_t)pl->nc[0] * pl->nc[1] * pl->nc[2] * nbatch * 2 * dtype_size(dtype);
+  int rc = dtype == FFB_F64 ? build_tables<double>(pl) : build_tables<float>(pl);
+  if (rc) { ffb_plan_destroy(pl); return rc; }
+  *out = pl;
+  return FFB_OK;
+}
+
+int ffb_plan_destroy(ffb_plan* pl) {
+  if (!pl) return FFB_OK;
+  if (pl->dtype == FFB_F64) free_tables<double>(pl); else free_tables<float>(pl);
+  for (int i = 0; i < 3; ++i) cudaFree(pl->ws[i]);
+  delete pl;
+  return FFB_OK;
+}
+
+int ffb_plan_workspace_bytes(const ffb_plan* pl, size_t* bytes) {
+  FFB_REQUIRE(pl && bytes, FFB_EINVAL, "NULL argument");
+  size_t b = 0;
+  for (int i = 0; i < 3; ++i) if (pl->ws[i]) b += pl->ws_bytes;
+  *bytes = b;
+  return FFB_OK;
+}
+
+int ffb_plan_describe(const ffb_plan* pl, char* buf, size_t buflen) {
+  FFB_REQUIRE(pl && buf && buflen, FFB_EINVAL, "NULL argument");
+  snprintf(buf, buflen, "%s", pl->desc.c_str());
+  return FFB_OK;
+}
+
+int ffb_fft_forward(ffb_plan* pl, const void* in, void* out) {
+  FFB_REQUIRE(pl && in && out, FFB_EINVAL, "NULL argument");
+  if (pl->kind == FFB_R2C) FFB_REQUIRE(in != out, FFB_EINVAL, "r2c transforms are out of place");
+  return pl->dtype == FFB_F64 ? exec<double>(pl, in, out, -1) : exec<float>(pl, in, out, -1);
+}
+
+int ffb_fft_inverse(ffb_plan* pl, const void* in, void* out) {
+  FFB_REQUIRE(pl && in && out, FFB_EINVAL, "NULL argument");
+  if (pl->kind == FFB_R2C) FFB_REQUIRE(in != out, FFB_EINVAL, "c2r transforms are out of place");
+  return pl->dtype == FFB_F64 ? exec<double>(pl, in, out, +1) : exec<float>(pl, in, out, +1);
+}
+
+}  // extern "C"

@@ -1,0 +1,225 @@
+// Register-resident Stockham FFT for power-of-two line lengths (sm_100a).
+//
+// One thread owns R points of one line for the whole transform; data stays in registers, shared memory is used
+// only for the inter-pass exchange (a pure permutation), so a line makes exactly one HBM round trip.
+//   pass p (radix r, Ns = product of earlier radices), butterfly j = t + b*N/R, b < R/r:
+//     in : x[j + k*N/r]                      = register  b + k*R/r      (the same registers in every pass)
+//     out: y[(j/Ns)*Ns*r + (j%Ns) + k*Ns]    -> scattered store to shared memory, then re-read at t + m*N/R
+//   first pass loads global memory at t + m*N/R, last pass lands on the same positions: both coalesced.
+// Exchange words are 8 bytes (Float64: re and im in two phases; Float32: one float2 phase) padded by one word
+// every 16, which the design model (tools/fft_model.py) shows to be bank-conflict free for every plan below.
+//
+// Modes (replace the cuFFT/FFTW plans of src/domains.jl:2-5 executed by mul!/ldiv!, src/diffusion.jl:137-139):
+//   C2C_ROWS : contiguous lines (x-dimension of `fftplan`, 1-D grids)
+//   C2C_COLS : strided lines; a CTA owns W adjacent columns so every HBM access is W*sizeof(complex) wide
+//   R2C      : real line of 2N reals -> N+1 complex (half spectrum), fused post-process
+//   C2R      : N+1 complex -> 2N reals, fused pre-process and 1/(nx*ny*nz) scaling
+#pragma once
+#include <type_traits>
+#include <utility>
+#include "fft_radix.cuh"
+
+namespace ffb {
+
+enum FftMode { C2C_ROWS = 0, C2C_COLS = 1, R2C_ROWS = 2, C2R_ROWS = 3 };
+
+template <typename T>
+struct Pow2Params {
+  const void* in;
+  void* out;
+  long long in_es, in_ls, in_os;     // element / line / outer strides of the input, in complex elements
+  long long out_es, out_ls, out_os;  // same for the output
+  long long nlines;                  // lines per outer index
+  int W;                             // lines per CTA
+  T scale;                           // applied to the output when != 1 (inverse normalisation)
+  const cx<T>* tw;                   // per-pass twiddles, forward sign: for each pass with Ns > 1, [(k-1)*Ns + a]
+  const cx<T>* twr;                  // exp(-i*pi*k/N), k < N, for the r2c / c2r split step
+};
+
+template <int... Rs> struct radix_product;
+template <> struct radix_product<> { static constexpr int value = 1; };
+template <int r, int... Rs> struct radix_product<r, Rs...> { static constexpr int value = r * radix_product<Rs...>::value; };
+
+__host__ __device__ constexpr int ce_log2(int v) { return v <= 1 ? 0 : 1 + ce_log2(v >> 1); }
+
+FFB_D int xpad(int i) { return i + (i >> 4); }
+__host__ __device__ constexpr int xpad_len(int n) { return n + (n >> 4) + 1; }
+
+// ---- exchange word access: F64 moves re / im separately, F32 moves the whole float2 ----
+template <typename T> struct xword;
+template <> struct xword<double> { using type = double; static constexpr int phases = 2; };
+template <> struct xword<float> { using type = float2; static constexpr int phases = 1; };
+
+template <typename T, int PH> FFB_D typename xword<T>::type xget(const cx<T>& c) {
+  if constexpr (sizeof(T) == 8) return PH == 0 ? c.x : c.y;
+  else return make_float2(c.x, c.y);
+}
+template <typename T, int PH> FFB_D void xput(cx<T>& c, typename xword<T>::type w) {
+  if constexpr (sizeof(T) == 8) { if (PH == 0) c.x = w; else c.y = w; }
+  else { c.x = w.x; c.y = w.y; }
+}
+
+template <int I, int N, typename F> FFB_D void static_for(F&& f) {
+  if constexpr (I < N) {
+    f(std::integral_constant<int, I>{});
+    static_for<I + 1, N>(f);
+  }
+}
+
+// Scatter the outputs of a pass into the exchange buffer and gather the inputs of the next pass.
+// COLS: word address = xpad(idx)*W + w (columns interleaved);  ROWS: w*xpad_len(N) + xpad(idx).
+template <typename T, bool COLS, int R, int N, int Ns, int r>
+FFB_D void exchange(cx<T> (&v)[R], int t, int w, int W, typename xword<T>::type* xb) {
+  constexpr int Tn = N / R, nb = R / r;
+  constexpr int lNs = ce_log2(Ns), lr = ce_log2(r);
+  auto addr = [&](int idx) { return COLS ? xpad(idx) * W + w : w * xpad_len(N) + xpad(idx); };
+  static_for<0, xword<T>::phases>([&](auto PH) {
+    constexpr int ph = decltype(PH)::value;
+    __syncthreads();  // previous gather finished before the buffer is overwritten
+#pragma unroll
+    for (int b = 0; b < nb; ++b) {
+      const int j = t + b * Tn;
+      const int base = ((j >> lNs) << (lNs + lr)) + (j & (Ns - 1));
+#pragma unroll
+      for (int k = 0; k < r; ++k) xb[addr(base + k * Ns)] = xget<T, ph>(v[b + k * nb]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < R; ++m) xput<T, ph>(v[m], xb[addr(t + m * Tn)]);
+  });
+}
+
+template <typename T, int DIR> FFB_D cx<T> load_tw(const cx<T>* p) {
+  using V = typename vec2<T>::type;
+  V q = __ldg(reinterpret_cast<const V*>(p));
+  return mk<T>(q.x, DIR < 0 ? q.y : -q.y);
+}
+
+// All passes of one line, recursively over the radix pack.  TWOFF = offset of this pass's twiddles in the table.
+template <typename T, int DIR, bool COLS, int R, int N, int Ns, int TWOFF, int r, int... Rest>
+FFB_D void run_passes(cx<T> (&v)[R], int t, int w, int W, typename xword<T>::type* xb, const cx<T>* tw) {
+  constexpr int Tn = N / R, nb = R / r;
+  static_for<0, nb>([&](auto B) {
+    constexpr int b = decltype(B)::value;
+    if constexpr (Ns > 1) {
+      const int a = (t + b * Tn) & (Ns - 1);
+#pragma unroll
+      for (int k = 1; k < r; ++k) v[b + k * nb] = v[b + k * nb] * load_tw<T, DIR>(tw + TWOFF + (k - 1) * Ns + a);
+    }
+    bfly_at<DIR, R, r, b>(v);
+  });
+  if constexpr (sizeof...(Rest) > 0) {
+    exchange<T, COLS, R, N, Ns, r>(v, t, w, W, xb);
+    run_passes<T, DIR, COLS, R, N, Ns * r, TWOFF + (Ns > 1 ? (r - 1) * Ns : 0), Rest...>(v, t, w, W, xb, tw);
+  }
+}
+
+template <typename T> FFB_D cx<T> ldc(const cx<T>* p) {
+  using V = typename vec2<T>::type;
+  V q = *reinterpret_cast<const V*>(p);
+  return mk<T>(q.x, q.y);
+}
+template <typename T> FFB_D void stc(cx<T>* p, cx<T> c) {
+  using V = typename vec2<T>::type;
+  V q; q.x = c.x; q.y = c.y;
+  *reinterpret_cast<V*>(p) = q;
+}
+
+template <typename T, int DIR, int MODE, int MAXT, int MINB, int R, int... Rs>
+__global__ void __launch_bounds__(MAXT, MINB) fft_pow2_kernel(const Pow2Params<T> p) {
+  constexpr int N = radix_product<Rs...>::value;
+  constexpr int Tn = N / R;
+  constexpr bool COLS = (MODE == C2C_COLS);
+  static_assert(N % R == 0, "R must divide N");
+  using XW = typename xword<T>::type;
+  extern __shared__ __align__(16) unsigned char ffb_smem[];
+  XW* xb = reinterpret_cast<XW*>(ffb_smem);
+
+  const int W = p.W;
+  const int tid = threadIdx.x;
+  const int w = COLS ? tid % W : tid / Tn;
+  const int t = COLS ? tid / W : tid % Tn;
+  const long long line = (long long)blockIdx.x * W + w;
+  const bool active = line < p.nlines;
+  const long long outer = blockIdx.y;
+
+  cx<T> v[R];
+  // ---------------- load ----------------
+  if constexpr (MODE == C2R_ROWS) {
+    // Z[k] = (X[k] + conj(X[N-k])) + i*exp(+i*pi*k/N)*(X[k] - conj(X[N-k]))
+    const cx<T>* in = reinterpret_cast<const cx<T>*>(p.in) + outer * p.in_os + line * p.in_ls;
+#pragma unroll
+    for (int m = 0; m < R; ++m) {
+      const int k = t + m * Tn;
+      cx<T> a = mk<T>(0, 0), b = mk<T>(0, 0);
+      if (active) { a = ldc(in + k); b = ldc(in + (N - k)); }
+      const cx<T> wk = conj(load_tw<T, -1>(p.twr + k));
+      const cx<T> s = a + conj(b), d = a - conj(b);
+      v[m] = s + mul_i(wk * d);
+    }
+  } else {
+    const cx<T>* in = reinterpret_cast<const cx<T>*>(p.in) + outer * p.in_os + line * p.in_ls;
+#pragma unroll
+    for (int m = 0; m < R; ++m) v[m] = active ? ldc(in + (long long)(t + m * Tn) * p.in_es) : mk<T>(0, 0);
+  }
+  // ---------------- transform ----------------
+  run_passes<T, DIR, COLS, R, N, 1, 0, Rs...>(v, t, w, W, xb, p.tw);
+  // ---------------- store ----------------
+  if constexpr (MODE == R2C_ROWS) {
+    // X[k] = 1/2 [ (Z[k] + conj(Z[N-k])) - i*exp(-i*pi*k/N)*(Z[k] - conj(Z[N-k])) ],  k = 0..N
+    // Z is staged once in shared memory (Float64: separate re / im planes) so the partner Z[N-k] can be read back.
+    constexpr int PL = xword<T>::phases;
+    const int plane = xpad_len(N) * W;
+    auto addr = [&](int idx) { return w * xpad_len(N) + xpad(idx); };
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < R; ++m) {
+      xb[addr(t + m * Tn)] = xget<T, 0>(v[m]);
+      if constexpr (PL == 2) xb[plane + addr(t + m * Tn)] = xget<T, 1>(v[m]);
+    }
+    __syncthreads();
+    cx<T>* out = reinterpret_cast<cx<T>*>(p.out) + outer * p.out_os + line * p.out_ls;
+    const T half = T(0.5);
+#pragma unroll
+    for (int m = 0; m < R; ++m) {
+      const int k = t + m * Tn;
+      const int kp = (N - k) & (N - 1);
+      cx<T> zp;
+      xput<T, 0>(zp, xb[addr(kp)]);
+      if constexpr (PL == 2) xput<T, 1>(zp, xb[plane + addr(kp)]);
+      const cx<T> wk = load_tw<T, -1>(p.twr + k);
+      const cx<T> s = v[m] + conj(zp), d = v[m] - conj(zp);
+      const cx<T> x = half * (s + mul_mi(wk * d));
+      if (active) {
+        stc(out + k, x);
+        if (k == 0) stc(out + N, mk<T>(v[m].x - v[m].y, T(0)));
+      }
+    }
+  } else if constexpr (MODE == C2R_ROWS) {
+    if (active) {
+      cx<T>* out = reinterpret_cast<cx<T>*>(p.out) + outer * p.out_os + line * p.out_ls;
+      const T sc = p.scale;
+#pragma unroll
+      for (int m = 0; m < R; ++m) stc(out + (t + m * Tn), sc * v[m]);
+    }
+  } else {
+    if (active) {
+      cx<T>* out = reinterpret_cast<cx<T>*>(p.out) + outer * p.out_os + line * p.out_ls;
+      const T sc = p.scale;
+      if (sc != T(1)) {
+#pragma unroll
+        for (int m = 0; m < R; ++m) stc(out + (long long)(t + m * Tn) * p.out_es, sc * v[m]);
+      } else {
+#pragma unroll
+        for (int m = 0; m < R; ++m) stc(out + (long long)(t + m * Tn) * p.out_es, v[m]);
+      }
+    }
+  }
+}
+
+// shared-memory bytes needed by a launch with W lines per CTA (the r2c split step stages full complex values)
+template <typename T> constexpr size_t pow2_smem_bytes(int N, int W, int mode) {
+  return (size_t)xpad_len(N) * W * 8 * ((mode == R2C_ROWS && sizeof(T) == 8) ? 2 : 1);
+}
+
+}  // namespace ffb

@@ -1,0 +1,401 @@
+// C-driven problem: `Problem(eqn, stepper, dt, grid, vars, params)` (src/problem.jl:99-111), `stepforward!`
+// (src/timesteppers.jl:6-35, one method per stepper :111-667) and `step_until!` (:734-760), with the calcN!
+// implementations of the benchmark equations built from library kernels.  The whole step is enqueued on the
+// library stream without host synchronisation.
+#include <cmath>
+#include <cstring>
+#include <vector>
+#include "ffb_common.cuh"
+
+namespace ffb {
+
+// ---------------------------------------------------------------- fused calcN! kernels (2-D vorticity)
+// uh = im*l*invKrsq*sol ; vh = -im*kr*invKrsq*sol   (GeophysicalFlows TwoDNavierStokes.calcN_advection!)
+template <typename T>
+__global__ void vort_prep_kernel(cx<T>* uh, cx<T>* vh, const cx<T>* sol, const T* invK, const T* kr, const T* l, long long n0) {
+  const long long row = blockIdx.x;
+  const T lv = l[row];
+  for (long long i = threadIdx.x; i < n0; i += blockDim.x) {
+    const long long idx = row * n0 + i;
+    const cx<T> s = sol[idx];
+    const T w = invK[idx];
+    const T lw = lv * w, kw = kr[i] * w;
+    uh[idx] = mk<T>(-(lw * s.y), lw * s.x);
+    vh[idx] = mk<T>(kw * s.y, -(kw * s.x));
+  }
+}
+// u *= zeta ; v *= zeta
+template <typename T>
+__global__ void mul2_real_kernel(T* u, T* v, const T* z, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const T zz = z[i];
+    u[i] = u[i] * zz;
+    v[i] = v[i] * zz;
+  }
+}
+// N = -im*kr*uh - im*l*vh ; dealias!(N, grid)
+template <typename T>
+__global__ void vort_combine_kernel(cx<T>* N, const cx<T>* uh, const cx<T>* vh, const T* kr, const T* l, long long n0, int lo0, int hi0,
+                                    int lo1, int hi1) {
+  const long long row = blockIdx.x;
+  const bool whole = lo1 > 0 && row >= lo1 - 1 && row < hi1;
+  const T lv = l[row];
+  for (long long i = threadIdx.x; i < n0; i += blockDim.x) {
+    const long long idx = row * n0 + i;
+    if (whole || (lo0 > 0 && i >= lo0 - 1 && i < hi0)) { N[idx] = mk<T>(0, 0); continue; }
+    const cx<T> a = uh[idx], b = vh[idx];
+    const T k = kr[i];
+    N[idx] = mk<T>(k * a.y + lv * b.y, -(k * a.x) - lv * b.x);
+  }
+}
+template <typename T>
+__global__ void square_real_kernel(T* c, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) { const T v = c[i]; c[i] = v * v; }
+}
+
+}  // namespace ffb
+
+using namespace ffb;
+
+struct ffb_problem {
+  ffb_problem_config cfg;
+  ffb_desc desc;
+  int nd, dtype;
+  long long n[3], nkr, nspec, nphys;
+  size_t sbytes, pbytes, rbytes;  // complex spectral array, real physical array, real spectral-shaped array
+  void *kr, *l, *m, *Krsq, *invKrsq, *Ldense, *filter;
+  ffb_coef L, cE, cE2, cz, ca, cb, cg;
+  void *E, *E2, *zeta, *alpha, *beta, *gamma;
+  ffb_plan* plan;
+  void* sol;
+  void* arr[6];            // stepper arrays
+  void *sh1, *sh2;         // spectral scratch (uh, vh / cxh)
+  void *ph1, *ph2, *ph3;   // physical scratch (u, v, zeta / cx)
+  double t, dt;
+  int64_t step;
+  size_t device_bytes;
+  std::vector<void*> owned;
+};
+
+namespace ffb {
+
+static double roundT(const ffb_problem* p, double v) { return p->dtype == FFB_F32 ? (double)(float)v : v; }
+
+static int dalloc(ffb_problem* p, void** ptr, size_t bytes, bool zero) {
+  int rc = ffb_malloc(ptr, bytes);
+  if (rc) return rc;
+  p->owned.push_back(*ptr);
+  p->device_bytes += bytes;
+  if (zero) return ffb_memset_zero(*ptr, bytes);
+  return FFB_OK;
+}
+
+template <typename T>
+static int calcN_impl(ffb_problem* p, void* N, const void* sol, double t) {
+  cudaStream_t s = current_stream();
+  const ffb_desc* d = &p->desc;
+  const long long n0 = d->dims[0];
+  int rc;
+  switch (p->cfg.calcN) {
+    case FFB_CALCN_CALLBACK:
+      FFB_REQUIRE(p->cfg.callback, FFB_EINVAL, "calcN callback is NULL");
+      return p->cfg.callback(N, sol, t, p->cfg.user);
+    case FFB_CALCN_ZERO:
+      return ffb_memset_zero(N, p->sbytes);
+    case FFB_CALCN_DIFFUSION:
+      // src/diffusion.jl:135-143
+      if ((rc = ffb_ew_spectral_mul(p->sh1, sol, 0.0, 1.0, p->kr, 1, nullptr, 0, nullptr, 0, nullptr, 0, 0, d))) return rc;
+      if ((rc = ffb_fft_inverse(p->plan, p->sh1, p->ph1))) return rc;
+      if ((rc = ffb_ew_mul_real(p->ph1, p->ph1, p->cfg.kappa, p->dtype, p->nphys))) return rc;
+      if ((rc = ffb_fft_forward(p->plan, p->ph1, p->sh1))) return rc;
+      return ffb_ew_spectral_mul(N, p->sh1, 0.0, 1.0, p->kr, 1, nullptr, 0, nullptr, 0, nullptr, 0, 0, d);
+    case FFB_CALCN_VORTICITY2D: {
+      const unsigned rows = (unsigned)d->dims[1];
+      vort_prep_kernel<T><<<rows, 256, 0, s>>>((cx<T>*)p->sh1, (cx<T>*)p->sh2, (const cx<T>*)sol, (const T*)p->invKrsq, (const T*)p->kr, (const T*)p->l, n0);
+      count_launch();
+      FFB_CHECK_LAUNCH();
+      if ((rc = ffb_fft_inverse(p->plan, p->sh1, p->ph1))) return rc;   // u
+      if ((rc = ffb_fft_inverse(p->plan, p->sh2, p->ph2))) return rc;   // v
+      if ((rc = ffb_fft_inverse(p->plan, sol, p->ph3))) return rc;      // zeta (zeta_h = sol; the transform preserves its input)
+      const unsigned blocks = (unsigned)std::min<long long>((p->nphys + 255) / 256, (long long)num_sms() * 16);
+      mul2_real_kernel<T><<<blocks, 256, 0, s>>>((T*)p->ph1, (T*)p->ph2, (const T*)p->ph3, p->nphys);
+      count_launch();
+      FFB_CHECK_LAUNCH();
+      if ((rc = ffb_fft_forward(p->plan, p->ph1, p->sh1))) return rc;
+      if ((rc = ffb_fft_forward(p->plan, p->ph2, p->sh2))) return rc;
+      vort_combine_kernel<T><<<rows, 256, 0, s>>>((cx<T>*)N, (const cx<T>*)p->sh1, (const cx<T>*)p->sh2, (const T*)p->kr, (const T*)p->l, n0,
+                                                  d->alias_lo[0], d->alias_hi[0], d->alias_lo[1], d->alias_hi[1]);
+      count_launch();
+      FFB_CHECK_LAUNCH();
+      return FFB_OK;
+    }
+    case FFB_CALCN_BURGERS3D: {
+      // N = -1/2 im kr rfft(irfft(sol)^2) ; dealias!(N, grid)   (builder-defined 3-D test equation)
+      if ((rc = ffb_fft_inverse(p->plan, sol, p->ph1))) return rc;
+      const unsigned blocks = (unsigned)std::min<long long>((p->nphys + 255) / 256, (long long)num_sms() * 16);
+      square_real_kernel<T><<<blocks, 256, 0, s>>>((T*)p->ph1, p->nphys);
+      count_launch();
+      FFB_CHECK_LAUNCH();
+      if ((rc = ffb_fft_forward(p->plan, p->ph1, p->sh1))) return rc;
+      return ffb_ew_spectral_mul(N, p->sh1, 0.0, -0.5, p->kr, 1, nullptr, 0, nullptr, 0, nullptr, 0, 1, d);
+    }
+  }
+  return set_error(FFB_EINVAL, "bad calcN kind %d", p->cfg.calcN);
+}
+
+static int calcN(ffb_problem* p, void* N, const void* sol, double t) {
+  return p->dtype == FFB_F64 ? calcN_impl<double>(p, N, sol, t) : calcN_impl<float>(p, N, sol, t);
+}
+
+// LSRK54 tableau (src/timesteppers.jl:335-350), rationals evaluated in Float64 then converted to T by the stage
+static const double kLsrkA[5] = {0.0, -567301805773.0 / 1357537059087.0, -2404267990393.0 / 2016746695238.0,
+                                 -3550918686646.0 / 2091501179385.0, -1275806237668.0 / 842570457699.0};
+static const double kLsrkB[5] = {1432997174477.0 / 9575080441755.0, 5161836677717.0 / 13612068292357.0, 1720146321549.0 / 2090206949498.0,
+                                 3134564353537.0 / 4481467310338.0, 2277821191437.0 / 14882151754819.0};
+static const double kLsrkC[5] = {0.0, 1432997174477.0 / 9575080441755.0, 2526269341429.0 / 6820363962896.0,
+                                 2006345519317.0 / 3224310063776.0, 2802321613138.0 / 2924317926251.0};
+
+static int step_once(ffb_problem* p) {
+  const int dt_ = p->dtype;
+  const int64_t n = p->nspec;
+  const double t = p->t, dt = p->dt;
+  const void* filt = p->cfg.filtered ? p->filter : nullptr;
+  int rc;
+  switch (p->cfg.stepper) {
+    case FFB_FORWARD_EULER:
+      if ((rc = calcN(p, p->arr[0], p->sol, t))) return rc;
+      if ((rc = ffb_stage_fe(p->sol, p->arr[0], &p->L, dt, filt, dt_, n))) return rc;
+      break;
+    case FFB_RK4: {
+      void *sol1 = p->arr[0], *r1 = p->arr[1], *r2 = p->arr[2], *r3 = p->arr[3], *r4 = p->arr[4];
+      const double h = roundT(p, dt / 2);
+      if ((rc = calcN(p, r1, p->sol, t))) return rc;
+      if ((rc = ffb_stage_rk4_substep(sol1, r1, p->sol, p->sol, &p->L, h, dt_, n))) return rc;
+      if ((rc = calcN(p, r2, sol1, roundT(p, t + h)))) return rc;
+      if ((rc = ffb_stage_rk4_substep(sol1, r2, sol1, p->sol, &p->L, h, dt_, n))) return rc;
+      if ((rc = calcN(p, r3, sol1, roundT(p, t + h)))) return rc;
+      if ((rc = ffb_stage_rk4_substep(sol1, r3, sol1, p->sol, &p->L, dt, dt_, n))) return rc;
+      if ((rc = calcN(p, r4, sol1, roundT(p, t + dt)))) return rc;
+      if ((rc = ffb_stage_rk4_final(p->sol, r1, r2, r3, r4, sol1, &p->L, dt, filt, 0, dt_, n))) return rc;
+      break;
+    }
+    case FFB_LSRK54: {
+      void *S2 = p->arr[0], *rhs = p->arr[1];
+      for (int i = 0; i < 5; ++i) {
+        const double ci = roundT(p, kLsrkC[i]);
+        if ((rc = calcN(p, rhs, p->sol, roundT(p, t + roundT(p, ci * dt))))) return rc;
+        if ((rc = ffb_stage_lsrk54(p->sol, S2, rhs, &p->L, kLsrkA[i], kLsrkB[i], dt, i == 0, i == 4 ? filt : nullptr, dt_, n))) return rc;
+      }
+      break;
+    }
+    case FFB_ETDRK4: {
+      void *sol1 = p->arr[0], *sol2 = p->arr[1], *N1 = p->arr[2], *N2 = p->arr[3], *N3 = p->arr[4], *N4 = p->arr[5];
+      if ((rc = calcN(p, N1, p->sol, t))) return rc;
+      if ((rc = ffb_stage_etdrk4_substep12(sol1, &p->cE2, p->sol, &p->cz, N1, dt_, n))) return rc;
+      const double t2 = roundT(p, t + roundT(p, dt / 2));
+      if ((rc = calcN(p, N2, sol1, t2))) return rc;
+      if ((rc = ffb_stage_etdrk4_substep12(sol2, &p->cE2, p->sol, &p->cz, N2, dt_, n))) return rc;
+      if ((rc = calcN(p, N3, sol2, t2))) return rc;
+      if ((rc = ffb_stage_etdrk4_substep3(sol2, &p->cE2, sol1, &p->cz, N1, N3, dt_, n))) return rc;
+      if ((rc = calcN(p, N4, sol2, roundT(p, t + dt)))) return rc;
+      if ((rc = ffb_stage_etdrk4_update(p->sol, &p->cE, &p->ca, &p->cb, &p->cg, N1, N2, N3, N4, filt, dt_, n))) return rc;
+      break;
+    }
+    case FFB_AB3: {
+      void *rhs = p->arr[0], *m1 = p->arr[1], *m2 = p->arr[2];
+      if ((rc = calcN(p, rhs, p->sol, t))) return rc;
+      if ((rc = ffb_stage_ab3(p->sol, rhs, m1, m2, &p->L, dt, p->step, filt, dt_, n))) return rc;
+      // RHS_2 <- RHS_1 ; RHS_1 <- RHS (after the clock tick, :644-648): rotate the pointers instead of copying
+      p->arr[0] = m2; p->arr[1] = rhs; p->arr[2] = m1;
+      break;
+    }
+    default:
+      return set_error(FFB_EINVAL, "bad stepper %d", p->cfg.stepper);
+  }
+  p->t = roundT(p, p->t + p->dt);
+  p->step += 1;
+  return FFB_OK;
+}
+
+}  // namespace ffb
+
+extern "C" {
+
+int ffb_problem_destroy(ffb_problem* p) {
+  if (!p) return FFB_OK;
+  ffb_sync();
+  for (void* q : p->owned) cudaFree(q);
+  if (p->plan) ffb_plan_destroy(p->plan);
+  delete p;
+  return FFB_OK;
+}
+
+int ffb_problem_create(ffb_problem** out, const ffb_problem_config* cfg) {
+  FFB_REQUIRE(out && cfg, FFB_EINVAL, "NULL argument");
+  *out = nullptr;
+  FFB_REQUIRE(cfg->ndim >= 1 && cfg->ndim <= 3, FFB_EINVAL, "ndim must be 1..3");
+  FFB_REQUIRE(cfg->dtype == FFB_F32 || cfg->dtype == FFB_F64, FFB_EINVAL, "bad dtype");
+  FFB_REQUIRE(cfg->stepper >= FFB_FORWARD_EULER && cfg->stepper <= FFB_AB3, FFB_EINVAL, "bad stepper");
+  FFB_REQUIRE(cfg->aliased_fraction >= 0 && cfg->aliased_fraction < 1, FFB_EINVAL, "`aliased_fraction` must be in [0, 1)");
+  if (cfg->calcN == FFB_CALCN_VORTICITY2D) FFB_REQUIRE(cfg->ndim == 2, FFB_EINVAL, "vorticity equation needs a 2-D grid");
+  if (cfg->calcN == FFB_CALCN_DIFFUSION) FFB_REQUIRE(cfg->ndim == 1 && cfg->kappa, FFB_EINVAL, "array-kappa diffusion needs a 1-D grid and kappa");
+  for (int d = 0; d < cfg->ndim; ++d)
+    if (cfg->n[d] % 2 != 0) return set_error(FFB_EDOMAIN, "n[%d] = %lld must be even", d, (long long)cfg->n[d]);
+
+  auto* p = new ffb_problem();
+  p->cfg = *cfg;
+  p->nd = cfg->ndim; p->dtype = cfg->dtype;
+  p->plan = nullptr; p->device_bytes = 0;
+  const size_t es = dtype_size(cfg->dtype);
+  for (int d = 0; d < 3; ++d) p->n[d] = d < cfg->ndim ? cfg->n[d] : 1;
+  p->nkr = p->n[0] / 2 + 1;
+  p->nspec = p->nkr * p->n[1] * p->n[2];
+  p->nphys = p->n[0] * p->n[1] * p->n[2];
+  p->sbytes = (size_t)p->nspec * 2 * es; p->pbytes = (size_t)p->nphys * es; p->rbytes = (size_t)p->nspec * es;
+  ffb_desc& D = p->desc;
+  D.ndim = p->nd; D.dtype = p->dtype;
+  D.dims[0] = p->nkr; D.dims[1] = p->n[1]; D.dims[2] = p->n[2]; D.dims[3] = 1;
+  // getaliasedwavenumbers (src/domains.jl:408-421), evaluated in Float64
+  for (int d = 0; d < 3; ++d) { D.alias_lo[d] = 0; D.alias_hi[d] = 0; }
+  if (cfg->aliased_fraction > 0) {
+    const double Lf = (1 - cfg->aliased_fraction) / 2, Rf = (1 + cfg->aliased_fraction) / 2;
+    for (int d = 0; d < p->nd; ++d) {
+      D.alias_lo[d] = (int32_t)std::floor(Lf * (double)p->n[d]) + 1;
+      D.alias_hi[d] = d == 0 ? (int32_t)p->nkr : (int32_t)std::ceil(Rf * (double)p->n[d]);  // kralias = iL:nkr for the half spectrum
+    }
+  }
+#define FFB_TRY(x) do { int _rc = (x); if (_rc) { ffb_problem_destroy(p); return _rc; } } while (0)
+  FFB_TRY(ffb_plan_create(&p->plan, p->nd, cfg->n, p->dtype, FFB_R2C, 1, FFB_PLAN_DEFAULT));
+  // wavenumbers and Krsq / invKrsq
+  p->l = p->m = nullptr;
+  FFB_TRY(dalloc(p, &p->kr, (size_t)p->nkr * es, false));
+  FFB_TRY(ffb_wavenumbers(p->kr, p->n[0], cfg->L[0], p->dtype, 1));
+  if (p->nd >= 2) { FFB_TRY(dalloc(p, &p->l, (size_t)p->n[1] * es, false)); FFB_TRY(ffb_wavenumbers(p->l, p->n[1], cfg->L[1], p->dtype, 0)); }
+  if (p->nd >= 3) { FFB_TRY(dalloc(p, &p->m, (size_t)p->n[2] * es, false)); FFB_TRY(ffb_wavenumbers(p->m, p->n[2], cfg->L[2], p->dtype, 0)); }
+  p->Krsq = p->invKrsq = p->Ldense = p->filter = nullptr;
+  const bool need_inv = cfg->calcN == FFB_CALCN_VORTICITY2D;
+  if (need_inv) FFB_TRY(dalloc(p, &p->invKrsq, p->rbytes, false));
+  if (!cfg->scalar_zero_L) {
+    // L = -nu * Krsq  (`@. L = -κ * kr^2`, src/diffusion.jl:84): Krsq is formed in Ldense, then scaled in place
+    FFB_TRY(dalloc(p, &p->Ldense, p->rbytes, false));
+    FFB_TRY(ffb_ksq(p->Ldense, p->invKrsq, p->kr, p->l, p->m, &D));
+    FFB_TRY(ffb_ew_axpby(p->Ldense, -cfg->nu, p->Ldense, 0.0, nullptr, 0, p->dtype, p->nspec));
+    p->L.ptr = p->Ldense; p->L.kind = FFB_COEF_REAL; p->L.dtype = p->dtype; p->L.re = p->L.im = 0;
+  } else {
+    if (need_inv) FFB_TRY(ffb_ksq(nullptr, p->invKrsq, p->kr, p->l, p->m, &D));
+    p->L.ptr = nullptr; p->L.kind = FFB_COEF_SCALAR; p->L.dtype = p->dtype; p->L.re = p->L.im = 0;
+  }
+  if (cfg->filtered) {
+    FFB_TRY(dalloc(p, &p->filter, p->rbytes, false));
+    const double dx = roundT(p, cfg->L[0] / (double)p->n[0]), dy = roundT(p, cfg->L[1] / (double)p->n[1]), dz = roundT(p, cfg->L[2] / (double)p->n[2]);
+    const double order = cfg->filter_order > 0 ? cfg->filter_order : 4, innerK = cfg->filter_tol > 0 ? cfg->filter_innerK : 2.0 / 3.0;
+    const double outerK = cfg->filter_tol > 0 ? cfg->filter_outerK : 1.0, tol = cfg->filter_tol > 0 ? cfg->filter_tol : 1e-15;
+    FFB_TRY(ffb_make_filter(p->filter, p->kr, p->l, p->m, dx, p->nd >= 2 ? dy : 0, p->nd >= 3 ? dz : 0, order, innerK, outerK, tol, &D));
+  }
+  // state and stepper arrays (`zeros(dev, eqn.T, eqn.dims)`, src/problem.jl:108; @devzeros in each stepper constructor)
+  FFB_TRY(dalloc(p, &p->sol, p->sbytes, true));
+  static const int narr[5] = {1, 5, 2, 6, 3};
+  for (int i = 0; i < 6; ++i) p->arr[i] = nullptr;
+  for (int i = 0; i < narr[cfg->stepper]; ++i) FFB_TRY(dalloc(p, &p->arr[i], p->sbytes, true));
+  p->dt = roundT(p, cfg->dt); p->t = 0; p->step = 0;   // Clock{T}(dt, 0, 0), src/problem.jl:104
+  if (cfg->stepper == FFB_ETDRK4) {
+    const int cd = cfg->coef_dtype == FFB_F64 ? FFB_F64 : p->dtype;
+    ffb_coef* cs[6] = {&p->cE, &p->cE2, &p->cz, &p->ca, &p->cb, &p->cg};
+    void** ps[6] = {&p->E, &p->E2, &p->zeta, &p->alpha, &p->beta, &p->gamma};
+    if (p->L.kind == FFB_COEF_SCALAR) {
+      double hs[12];
+      FFB_TRY(ffb_etd_coeffs(cfg->dt, &p->L, p->dtype, cd, 1, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, hs));
+      for (int i = 0; i < 6; ++i) { cs[i]->ptr = nullptr; cs[i]->kind = FFB_COEF_SCALAR; cs[i]->dtype = cd; cs[i]->re = hs[2 * i]; cs[i]->im = hs[2 * i + 1]; *ps[i] = nullptr; }
+    } else {
+      const size_t cb = (size_t)p->nspec * dtype_size(cd);
+      for (int i = 0; i < 6; ++i) { FFB_TRY(dalloc(p, ps[i], cb, false)); cs[i]->ptr = *ps[i]; cs[i]->kind = FFB_COEF_REAL; cs[i]->dtype = cd; cs[i]->re = cs[i]->im = 0; }
+      FFB_TRY(ffb_etd_coeffs(cfg->dt, &p->L, p->dtype, cd, p->nspec, p->E, p->E2, p->zeta, p->alpha, p->beta, p->gamma, nullptr));
+    }
+  }
+  // vars
+  p->sh1 = p->sh2 = p->ph1 = p->ph2 = p->ph3 = nullptr;
+  FFB_TRY(dalloc(p, &p->ph1, p->pbytes, true));
+  if (cfg->calcN == FFB_CALCN_VORTICITY2D) {
+    FFB_TRY(dalloc(p, &p->sh1, p->sbytes, true)); FFB_TRY(dalloc(p, &p->sh2, p->sbytes, true));
+    FFB_TRY(dalloc(p, &p->ph2, p->pbytes, true)); FFB_TRY(dalloc(p, &p->ph3, p->pbytes, true));
+  } else if (cfg->calcN == FFB_CALCN_DIFFUSION || cfg->calcN == FFB_CALCN_BURGERS3D) {
+    FFB_TRY(dalloc(p, &p->sh1, p->sbytes, true));
+  }
+  FFB_TRY(ffb_sync());
+#undef FFB_TRY
+  *out = p;
+  return FFB_OK;
+}
+
+int ffb_problem_sol(ffb_problem* p, void** sol, int64_t* n) {
+  FFB_REQUIRE(p, FFB_EINVAL, "prob is NULL");
+  if (sol) *sol = p->sol;
+  if (n) *n = p->nspec;
+  return FFB_OK;
+}
+
+int ffb_problem_clock(ffb_problem* p, double* t, int64_t* step, double* dt) {
+  FFB_REQUIRE(p, FFB_EINVAL, "prob is NULL");
+  if (t) *t = p->t;
+  if (step) *step = p->step;
+  if (dt) *dt = p->dt;
+  return FFB_OK;
+}
+
+int ffb_problem_set_dt(ffb_problem* p, double dt) {
+  FFB_REQUIRE(p, FFB_EINVAL, "prob is NULL");
+  p->dt = roundT(p, dt);
+  return FFB_OK;
+}
+
+int ffb_problem_bytes(ffb_problem* p, size_t* b) {
+  FFB_REQUIRE(p && b, FFB_EINVAL, "NULL argument");
+  size_t ws = 0;
+  ffb_plan_workspace_bytes(p->plan, &ws);
+  *b = p->device_bytes + ws;
+  return FFB_OK;
+}
+
+int ffb_problem_set_physical(ffb_problem* p, const void* host_field) {
+  FFB_REQUIRE(p && host_field, FFB_EINVAL, "NULL argument");
+  int rc = ffb_h2d(p->ph1, host_field, p->pbytes);
+  if (rc) return rc;
+  return ffb_fft_forward(p->plan, p->ph1, p->sol);
+}
+
+int ffb_problem_get_physical(ffb_problem* p, void* host_field) {
+  FFB_REQUIRE(p && host_field, FFB_EINVAL, "NULL argument");
+  int rc = ffb_fft_inverse(p->plan, p->sol, p->ph1);
+  if (rc) return rc;
+  return ffb_d2h(host_field, p->ph1, p->pbytes);
+}
+
+int ffb_step(ffb_problem* p, int64_t nsteps) {
+  FFB_REQUIRE(p, FFB_EINVAL, "prob is NULL");
+  for (int64_t i = 0; i < nsteps; ++i) {
+    int rc = step_once(p);
+    if (rc) return rc;
+  }
+  return FFB_OK;
+}
+
+int ffb_step_until(ffb_problem* p, double stop_time) {
+  FFB_REQUIRE(p, FFB_EINVAL, "prob is NULL");
+  if (p->cfg.stepper == FFB_ETDRK4)
+    return set_error(FFB_ESTEPPER, "step_until! requires fully explicit time stepper; does not work with ETDRK4");
+  if (!(stop_time > p->t)) return set_error(FFB_EINVAL, "stop_time must be greater than prob.clock.t");
+  const double dt = p->dt;
+  const double time_interval = roundT(p, stop_time - p->t);
+  const int64_t nsteps = (int64_t)std::floor(roundT(p, time_interval / dt));
+  int rc = ffb_step(p, nsteps);
+  if (rc) return rc;
+  // `t_remaining = time_interval - prob.clock.t` (src/timesteppers.jl:752): only right when the run began at t = 0
+  p->dt = roundT(p, time_interval - p->t);
+  rc = ffb_step(p, 1);
+  p->dt = dt;
+  return rc;
+}
+
+}  // extern "C"
