@@ -62,8 +62,9 @@ __global__ void generic_c2r_pre_kernel(const cx<T>* __restrict__ x, cx<T>* __res
   if (gid >= nlines * N) return;
   const long long line = gid / N;
   const int k = (int)(gid % N);
-  const cx<T> xk = x[line * (N + 1) + k];
-  const cx<T> xc = conj(x[line * (N + 1) + (N - k)]);
+  cx<T> xk = x[line * (N + 1) + k];
+  cx<T> xc = conj(x[line * (N + 1) + (N - k)]);
+  if (k == 0) { xk.y = T(0); xc.y = T(0); }  // c2r ignores Im X[0] and Im X[N] (FFTW / cuFFT / pocketfft convention)
   const cx<T> w = conj(w2N[k]);
   const cx<T> s = xk + xc, d = xk - xc;
   z[line * N + k] = s + mul_i(w * d);

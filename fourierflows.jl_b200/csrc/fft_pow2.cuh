@@ -153,6 +153,7 @@ __global__ void __launch_bounds__(MAXT, MINB) fft_pow2_kernel(const Pow2Params<T
       const int k = t + m * Tn;
       cx<T> a = mk<T>(0, 0), b = mk<T>(0, 0);
       if (active) { a = ldc(in + k); b = ldc(in + (N - k)); }
+      if (k == 0) { a.y = T(0); b.y = T(0); }  // c2r ignores Im X[0] and Im X[N] (FFTW / cuFFT / pocketfft convention)
       const cx<T> wk = conj(load_tw<T, -1>(p.twr + k));
       const cx<T> s = a + conj(b), d = a - conj(b);
       v[m] = s + mul_i(wk * d);

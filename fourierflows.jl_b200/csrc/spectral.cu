@@ -352,15 +352,14 @@ int ffb_etd_coeffs(double dt, const ffb_coef* L, int dtype, int coef_dtype, int6
   FFB_REQUIRE(coef_dtype == FFB_F64 || coef_dtype == dtype, FFB_EINVAL, "coef_dtype must be Float64 or the state type");
   if (L->kind == FFB_COEF_SCALAR) {
     FFB_REQUIRE(host_scalars, FFB_EINVAL, "host_scalars is NULL for scalar L");
-    zc_t dtL;
-    if (dtype == FFB_F32) { const float d = (float)dt; dtL = {(double)(d * (float)L->re), (double)(d * (float)L->im)}; }
-    else dtL = {dt * L->re, dt * L->im};
-    const EtdOut o = etd_element(dtL);
+    // A scalar L arrives as a Float64 (or Int) value: Julia forms `dt * L` and `exp(dt * L)` in Float64 after
+    // converting dt to the problem's float type (src/timesteppers.jl:457,674-675,696).
     const double dtT = dtype == FFB_F32 ? (double)(float)dt : dt;
+    const zc_t dtL = {dtT * L->re, dtT * L->im};
+    const EtdOut o = etd_element(dtL);
     const zc_t v[6] = {o.E, o.E2, {dtT * o.zeta.x, dtT * o.zeta.y}, {dtT * o.alpha.x, dtT * o.alpha.y}, {dtT * o.beta.x, dtT * o.beta.y}, {dtT * o.gamma.x, dtT * o.gamma.y}};
     for (int i = 0; i < 6; ++i) {
       double re = v[i].x, im = v[i].y;
-      if (i < 2 && dtype == FFB_F32) { re = (double)(float)re; im = (double)(float)im; }
       if (L->im == 0.0) im = 0.0;  // real L: `real.(...)` (:710-715)
       host_scalars[2 * i] = re; host_scalars[2 * i + 1] = im;
     }

@@ -25,6 +25,7 @@ __all__ = [
     "dealias", "makefilter_K", "makefilter", "Equation", "Clock", "Problem", "TimeStepper", "stepforward",
     "step_until", "getetdcoeffs", "getexpLs", "STEPPERS", "isexplicit", "cxtype", "fltype",
     "Diffusion", "RfftPlan", "FftPlan", "set_fft_workers", "zeros", "LSRK54_A", "LSRK54_B", "LSRK54_C",
+    "TwoDNavierStokes", "Burgers3D", "random_phase_field",
 ]
 
 _WORKERS = os.cpu_count() or 1
@@ -637,3 +638,103 @@ class Diffusion:
         prob.vars.c[...] = c
         prob.grid.rfftplan.mul(prob.sol, prob.vars.c)
         Diffusion.updatevars(prob)
+
+
+# ----------------------------------------------------------------------------- benchmark equations
+class TwoDNavierStokes:
+    """2-D vorticity equation `calcN_advection!` of the child package the reference points to (README.md:81-83;
+    GeophysicalFlows TwoDNavierStokes, not in the reference tree) restated as in SURVEY 8d C3, followed by
+    `dealias!(N, grid)`; L = -nu * Krsq."""
+
+    @dataclass
+    class Params:
+        nu: float
+
+    @dataclass
+    class Vars:
+        zeta: np.ndarray
+        u: np.ndarray
+        v: np.ndarray
+        zetah: np.ndarray
+        uh: np.ndarray
+        vh: np.ndarray
+
+    @staticmethod
+    def calcN(N, sol, t, clock, vars, params, grid):
+        vars.uh[...] = ((1j * grid.l) * grid.invKrsq) * sol
+        vars.vh[...] = ((-1j * grid.kr) * grid.invKrsq) * sol
+        vars.zetah[...] = sol
+        grid.rfftplan.ldiv(vars.u, vars.uh)
+        grid.rfftplan.ldiv(vars.v, vars.vh)
+        grid.rfftplan.ldiv(vars.zeta, vars.zetah)
+        vars.u[...] = vars.u * vars.zeta
+        vars.v[...] = vars.v * vars.zeta
+        grid.rfftplan.mul(vars.uh, vars.u)
+        grid.rfftplan.mul(vars.vh, vars.v)
+        N[...] = (-1j * grid.kr) * vars.uh - (1j * grid.l) * vars.vh
+        dealias(N, grid)
+
+    @staticmethod
+    def Problem(nx=256, Lx=2 * np.pi, ny=None, Ly=None, nu=0.0, dt=0.01, stepper="RK4", aliased_fraction=1 / 3, T=np.float64,
+                **stepperkwargs):
+        grid = TwoDGrid(nx=nx, Lx=Lx, ny=ny, Ly=Ly, aliased_fraction=aliased_fraction, T=T)
+        T = grid.T
+        cT = cxtype(T)
+        vars = TwoDNavierStokes.Vars(*(zeros(T, (grid.nx, grid.ny)) for _ in range(3)), *(zeros(cT, (grid.nkr, grid.nl)) for _ in range(3)))
+        L = np.asfortranarray((T.type(-nu) * grid.Krsq).astype(T))
+        eqn = Equation(L, TwoDNavierStokes.calcN, grid)
+        return Problem(eqn, stepper, dt, grid, vars, TwoDNavierStokes.Params(nu), **stepperkwargs)
+
+
+class Burgers3D:
+    """Builder-defined 3-D test equation of SURVEY 8d C4/C5: N = -1/2 im kr rfft(irfft(sol)^2), `dealias!(N, grid)`,
+    L = -kappa * Krsq (the reference's Diffusion module is 1-D only)."""
+
+    @dataclass
+    class Params:
+        kappa: float
+
+    @dataclass
+    class Vars:
+        c: np.ndarray
+        ch: np.ndarray
+
+    @staticmethod
+    def calcN(N, sol, t, clock, vars, params, grid):
+        grid.rfftplan.ldiv(vars.c, sol)
+        vars.c[...] = vars.c * vars.c
+        grid.rfftplan.mul(vars.ch, vars.c)
+        N[...] = (-0.5j * grid.kr) * vars.ch
+        dealias(N, grid)
+
+    @staticmethod
+    def Problem(nx=64, Lx=2 * np.pi, ny=None, nz=None, kappa=1e-3, dt=1e-3, stepper="FilteredRK4", aliased_fraction=1 / 3,
+                T=np.float64, **stepperkwargs):
+        grid = ThreeDGrid(nx=nx, Lx=Lx, ny=ny, nz=nz, aliased_fraction=aliased_fraction, T=T)
+        T = grid.T
+        vars = Burgers3D.Vars(zeros(T, grid.shape), zeros(cxtype(T), (grid.nkr, grid.nl, grid.nm)))
+        L = np.asfortranarray((T.type(-kappa) * grid.Krsq).astype(T))
+        eqn = Equation(L, Burgers3D.calcN, grid)
+        return Problem(eqn, stepper, dt, grid, vars, Burgers3D.Params(kappa), **stepperkwargs)
+
+
+def random_phase_field(shape, Lext, K0, slope=1.0, seed=1234, T=np.float64):
+    """Synthetic random-phase real field: |f_hat| ~ K^slope * exp(-(K/K0)^2), phases U[0, 2pi),
+    Hermitian-consistent by construction (generated with irfftn on the host), normalised to rms 1."""
+    rng = np.random.default_rng(seed)
+    nd = len(shape)
+    Lext = (Lext,) * nd if np.isscalar(Lext) else tuple(Lext)
+    ks = [rfftfreq(shape[0], 2 * np.pi / Lext[0] * shape[0])] + [fftfreq(shape[d], 2 * np.pi / Lext[d] * shape[d]) for d in range(1, nd)]
+    K2 = np.zeros((shape[0] // 2 + 1,) + tuple(shape[1:]))
+    for d, k in enumerate(ks):
+        sh = [1] * nd
+        sh[d] = len(k)
+        K2 = K2 + (k * k).reshape(sh)
+    K = np.sqrt(K2)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        amp = np.where(K > 0, K ** slope * np.exp(-(K / K0) ** 2), 0.0)
+    fh = amp * np.exp(2j * np.pi * rng.random(K.shape))
+    axes = tuple(range(nd - 1, -1, -1))
+    f = sfft.irfftn(np.asfortranarray(fh), s=tuple(shape[ax] for ax in axes), axes=axes, workers=_WORKERS)
+    f = f / np.sqrt(np.mean(f * f))
+    return np.asfortranarray(f.astype(T))

@@ -1,0 +1,196 @@
+"""FFT parity through the C ABI (`ffb_plan_create` / `ffb_fft_forward` / `ffb_fft_inverse`).
+
+1. the reference's closed-form known-answer tests (test/test_fft.jl, test/test_ifft.jl, test/createffttestfunctions.jl)
+   at rtol 1e-12, sizes 1-D 32, 2-D 32x64, 3-D 32x30x16;
+2. parity with the CPU oracle (scipy.fft) on seeded random fields: rel-L2 <= 1e-12 (Float64), <= 1e-5 (Float32).
+"""
+import numpy as np
+import pytest
+
+import oracle as fo
+from util import TOL_FFT, isapprox, relerr
+
+pytestmark = pytest.mark.gpu
+rtol_fft = 1e-12  # test/runtests.jl:21
+
+
+@pytest.fixture(scope="module")
+def ff():
+    import fourierflows_jl_b200 as ff
+    assert ff.have_device(), "CUDA extension must be present on the GPU box (no fallback)"
+    return ff
+
+
+def dev(ff, a):
+    return ff.DevArray.from_numpy(np.asfortranarray(a))
+
+
+def test_kat_1d_cosmx(ff):
+    g = ff.OneDGrid(ff.GPU(), nx=32, Lx=2 * np.pi)
+    og = fo.OneDGrid(nx=32, Lx=2 * np.pi)
+    m, phi = 5, np.pi / 3
+    k0 = og.k[1]
+    assert np.array_equal(g.k.to_numpy(), og.k) and np.array_equal(g.kr.to_numpy(), og.kr)
+    f1 = np.cos(m * k0 * og.x + phi)
+    th = np.zeros(g.nk, dtype=complex)
+    thr = np.zeros(g.nkr, dtype=complex)
+    for i in range(g.nk):
+        if abs(og.k[i]) == m * k0:
+            th[i] = -np.exp(np.sign(og.k[i]) * 1j * phi) * g.nx / 2
+    for i in range(g.nkr):
+        if abs(og.k[i]) == m * k0:
+            thr[i] = -np.exp(np.sign(og.kr[i]) * 1j * phi) * g.nx / 2
+    f1h = (g.fftplan * dev(ff, f1.astype(complex))).to_numpy()
+    df1 = dev(ff, f1)
+    f1hr = (g.rfftplan * df1).to_numpy()
+    out = ff.DevArray.zeros(np.complex128, (g.nkr,))
+    ff.mul_(out, g.rfftplan, df1)                         # mul!(f1hr_mul, g.rfftplan, f1)
+    assert isapprox(f1h, th, rtol_fft)                    # test_fft_cosmx
+    assert isapprox(f1hr, thr, rtol_fft)                  # test_rfft_cosmx
+    assert isapprox(out.to_numpy(), thr, rtol_fft)        # test_rfft_mul_cosmx
+    assert isapprox(f1, g.fftplan.solve(dev(ff, f1h)).to_numpy().real, rtol_fft)   # test_ifft_cosmx
+    f1b = ff.DevArray.zeros(np.float64, (g.nx,))
+    ff.ldiv_(f1b, g.rfftplan, dev(ff, f1hr))              # test_irfft_mul_cosmx
+    assert isapprox(f1, f1b.to_numpy(), rtol_fft)
+
+
+def test_kat_2d(ff):
+    g = ff.TwoDGrid(ff.GPU(), nx=32, Lx=2 * np.pi, ny=64, Ly=3 * np.pi)
+    og = fo.TwoDGrid(nx=32, Lx=2 * np.pi, ny=64, Ly=3 * np.pi)
+    x, y = og.x.reshape(-1, 1), og.y.reshape(1, -1)
+    m, n = 5, 2
+    k0, l0 = og.k[1, 0], og.l[0, 1]
+    f1 = np.cos(m * k0 * x) * np.cos(n * l0 * y)
+    f2 = np.sin(m * k0 * x + n * l0 * y)
+    sh, shr = (g.nk, g.nl), (g.nkr, g.nl)
+    K, Lw = np.broadcast_to(og.k, sh), np.broadcast_to(og.l, sh)
+    Kr, Lr = np.broadcast_to(og.kr, shr), np.broadcast_to(og.l, shr)
+    f1h_th = np.where((np.abs(K) == m * k0) & (np.abs(Lw) == n * l0), -g.nx * g.ny / 4, 0).astype(complex)
+    f2h_th = -1j * (np.where((K == m * k0) & (Lw == n * l0), -g.nx * g.ny / 2, 0) + np.where((K == -m * k0) & (Lw == -n * l0), g.nx * g.ny / 2, 0))
+    f1hr_th = np.where((np.abs(Kr) == m * k0) & (np.abs(Lr) == n * l0), -g.nx * g.ny / 4, 0).astype(complex)
+    f2hr_th = -1j * np.where((Kr == m * k0) & (Lr == n * l0), -g.nx * g.ny / 2, 0)
+    assert isapprox((g.fftplan * dev(ff, f1.astype(complex))).to_numpy(), f1h_th, rtol_fft)
+    assert isapprox((g.fftplan * dev(ff, f2.astype(complex))).to_numpy(), f2h_th, rtol_fft)
+    for f, th in ((f1, f1hr_th), (f2, f2hr_th)):
+        fh = g.rfftplan * dev(ff, f)
+        assert isapprox(fh.to_numpy(), th, rtol_fft)
+        fb = ff.DevArray.zeros(np.float64, (g.nx, g.ny))
+        g.rfftplan.ldiv(fb, fh)
+        assert isapprox(f, fb.to_numpy(), rtol_fft)
+        assert isapprox(f, g.fftplan.solve(g.fftplan * dev(ff, f.astype(complex))).to_numpy().real, rtol_fft)
+
+
+def test_kat_3d_32x30x16(ff):
+    kw = dict(nx=32, Lx=2 * np.pi, ny=30, Ly=3 * np.pi, nz=16, Lz=4.0)
+    g = ff.ThreeDGrid(ff.GPU(), **kw)
+    og = fo.ThreeDGrid(**kw)
+    x, y, z = og.x.reshape(-1, 1, 1), og.y.reshape(1, -1, 1), og.z.reshape(1, 1, -1)
+    mx, my, mz = 5, 2, 3
+    k0, l0, m0 = og.k[1, 0, 0], og.l[0, 1, 0], og.m[0, 0, 1]
+    f1 = np.cos(mx * k0 * x) * np.cos(my * l0 * y) * np.cos(mz * m0 * z)
+    f2 = np.sin(mx * k0 * x + my * l0 * y + mz * m0 * z)
+    shr = (g.nkr, g.nl, g.nm)
+    Kr, Lr, Mr = np.broadcast_to(og.kr, shr), np.broadcast_to(og.l, shr), np.broadcast_to(og.m, shr)
+    N3 = g.nx * g.ny * g.nz
+    f1hr_th = np.where((np.abs(Kr) == mx * k0) & (np.abs(Lr) == my * l0) & (np.abs(Mr) == mz * m0), N3 / 8, 0).astype(complex)
+    f2hr_th = -1j * np.where((Kr == mx * k0) & (Lr == my * l0) & (Mr == mz * m0), N3 / 2, 0)
+    for f, th in ((f1, f1hr_th), (f2, f2hr_th)):
+        fh = g.rfftplan * dev(ff, f)
+        assert isapprox(fh.to_numpy(), th, rtol_fft)
+        assert isapprox(f, g.rfftplan.solve(fh).to_numpy(), rtol_fft)
+    sh = (g.nk, g.nl, g.nm)
+    K, Lw, M = np.broadcast_to(og.k, sh), np.broadcast_to(og.l, sh), np.broadcast_to(og.m, sh)
+    f1h_th = np.where((np.abs(K) == mx * k0) & (np.abs(Lw) == my * l0) & (np.abs(M) == mz * m0), N3 / 8, 0).astype(complex)
+    f1h = g.fftplan * dev(ff, f1.astype(complex))
+    assert isapprox(f1h.to_numpy(), f1h_th, rtol_fft)
+    assert isapprox(f1, g.fftplan.solve(f1h).to_numpy().real, rtol_fft)
+
+
+SHAPES = [(4,), (6,), (16,), (30,), (34,), (256,), (1024,), (8192,), (16384,), (32768,), (6, 8), (32, 64), (34, 16), (512, 256), (64, 4096),
+          (2048, 32), (6, 8, 10), (32, 30, 16), (64, 32, 128), (256, 16, 16)]
+
+
+@pytest.mark.parametrize("T", [np.float64, np.float32])
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_rfft_matches_oracle(ff, shape, T):
+    """ragged / non-power-of-two / maximum in-kernel sizes, both precisions; the input of the inverse is preserved"""
+    rng = np.random.default_rng(7)
+    x = np.asfortranarray(rng.standard_normal(shape).astype(T))
+    oplan = fo.RfftPlan(shape, T)
+    ref = oplan * x.astype(np.float64)
+    plan = ff.Plan(shape, T, ff._lib.FFB_R2C)
+    dx = dev(ff, x)
+    xh = plan * dx
+    tol = TOL_FFT[np.dtype(T)]
+    assert relerr(xh.to_numpy(), ref) <= tol
+    assert np.array_equal(dx.to_numpy(), x)
+    before = xh.to_numpy()
+    back = plan.solve(xh)
+    assert relerr(back.to_numpy(), x) <= tol
+    assert np.array_equal(xh.to_numpy(), before), "ldiv! must preserve its input in this implementation"
+
+
+@pytest.mark.parametrize("T", [np.float64, np.float32])
+@pytest.mark.parametrize("shape", [(2,), (30,), (64,), (8192,), (16384,), (16, 30), (128, 64), (8, 8, 8), (32, 30, 16)], ids=lambda s: "x".join(map(str, s)))
+def test_fft_c2c_matches_oracle(ff, shape, T):
+    rng = np.random.default_rng(8)
+    cT = np.complex64 if T == np.float32 else np.complex128
+    x = np.asfortranarray((rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).astype(cT))
+    ref = fo.FftPlan(shape, T) * x.astype(np.complex128)
+    plan = ff.Plan(shape, T, ff._lib.FFB_C2C)
+    xh = plan * dev(ff, x)
+    tol = TOL_FFT[np.dtype(T)]
+    assert relerr(xh.to_numpy(), ref) <= tol
+    assert relerr(plan.solve(xh).to_numpy(), x) <= tol
+    # in place
+    d = dev(ff, x)
+    plan.mul(d, d)
+    assert relerr(d.to_numpy(), ref) <= tol
+
+
+def test_generic_and_register_paths_agree(ff):
+    """the arbitrary-size path is an independent implementation: both must agree on power-of-two sizes"""
+    rng = np.random.default_rng(9)
+    x = np.asfortranarray(rng.standard_normal((256, 128)))
+    a = ff.Plan((256, 128), np.float64, ff._lib.FFB_R2C)
+    b = ff.Plan((256, 128), np.float64, ff._lib.FFB_R2C, flags=ff._lib.FFB_PLAN_FORCE_GENERIC)
+    assert "pow2" in a.describe() and "pow2" not in b.describe()
+    assert relerr((a * dev(ff, x)).to_numpy(), (b * dev(ff, x)).to_numpy()) <= 1e-14
+
+
+def test_batched_fields(ff):
+    """trailing field dimension (examples/OneDShallowWaterGeostrophicAdjustment.jl:114-126 shape requirement)"""
+    rng = np.random.default_rng(10)
+    x = np.asfortranarray(rng.standard_normal((64, 32, 3)))
+    plan = ff.Plan((64, 32), np.float64, ff._lib.FFB_R2C, nbatch=3)
+    xh = (plan * dev(ff, x)).to_numpy()
+    op = fo.RfftPlan((64, 32), np.float64)
+    for f in range(3):
+        assert relerr(xh[:, :, f], op * x[:, :, f]) <= 1e-13
+
+
+def test_odd_sizes_raise_domain_error(ff):
+    """runtests.jl:133-138"""
+    for shape in ((5,), (5, 4), (4, 5), (5, 4, 6), (4, 5, 6), (4, 6, 5)):
+        with pytest.raises(ff.DomainError):
+            ff.Plan(shape, np.float64, ff._lib.FFB_R2C)
+    with pytest.raises(ff.DomainError):
+        ff.OneDGrid(ff.GPU(), nx=5, Lx=1)
+    with pytest.raises(ff.DomainError):
+        ff.TwoDGrid(ff.GPU(), nx=4, Lx=1, ny=5, Ly=2)
+    with pytest.raises(ff.DomainError):
+        ff.ThreeDGrid(ff.GPU(), nx=4, Lx=1, ny=6, Ly=2, nz=5, Lz=3)
+
+
+@pytest.mark.parametrize("shape", [(64,), (64, 64), (30, 16), (16, 8, 8)], ids=lambda s: "x".join(map(str, s)))
+def test_c2r_ignores_non_hermitian_parts_like_fftw(ff, shape):
+    """`ldiv!` on a spectrum that is not Hermitian-consistent (e.g. `-im*kr*...` at the Nyquist column, as every
+    calcN! produces): FFTW, cuFFT and pocketfft ignore Im X[0] and Im X[nx/2] of each x-line; so must we."""
+    rng = np.random.default_rng(21)
+    sh = (shape[0] // 2 + 1,) + tuple(shape[1:])
+    xh = np.asfortranarray(rng.standard_normal(sh) + 1j * rng.standard_normal(sh))
+    ref = fo.RfftPlan(shape, np.float64).solve(xh)
+    plan = ff.Plan(shape, np.float64, ff._lib.FFB_R2C)
+    assert relerr(plan.solve(dev(ff, xh)).to_numpy(), ref) <= 1e-13
+    gen = ff.Plan(shape, np.float64, ff._lib.FFB_R2C, flags=ff._lib.FFB_PLAN_FORCE_GENERIC)
+    assert relerr(gen.solve(dev(ff, xh)).to_numpy(), ref) <= 1e-13
