@@ -8,7 +8,7 @@ Julia wrapper is `julia/FourierFlowsB200.jl`).  Julia's `f!`
 The directory name contains a dot, so import it through the `fourierflows_jl_b200` alias module at the repo root.
 """
 from . import _lib
-from ._lib import DomainError, FFBError, have_device, launch_count
+from ._lib import DomainError, FFBError, have_device, launch_count, prof_enable, prof_report
 from .array import CPU, GPU, DevArray, cxtype, device_array, devzeros, fltype, zeros
 from .domains import (OneDGrid, Plan, ThreeDGrid, TwoDGrid, dealias, getaliasedwavenumbers, gridpoints, ldiv_,
                       makefilter, mul_)

@@ -65,6 +65,8 @@ SIGNATURES = {
     "ffb_get_stream": [_P(_vp)],
     "ffb_sync": [],
     "ffb_launch_count": [_P(C.c_uint64)],
+    "ffb_prof_enable": [_i],
+    "ffb_prof_report": [C.c_char_p, _sz],
     "ffb_malloc": [_P(_vp), _sz],
     "ffb_free": [_vp],
     "ffb_memset_zero": [_vp, _sz],
@@ -152,6 +154,17 @@ def have_device() -> bool:
         return load().ffb_device_count(C.byref(n)) == 0 and n.value > 0
     except (OSError, FFBError):
         return False
+
+
+def prof_enable(on: bool) -> None:
+    call("ffb_prof_enable", 1 if on else 0)
+
+
+def prof_report():
+    import json
+    buf = C.create_string_buffer(1 << 16)
+    call("ffb_prof_report", buf, 1 << 16)
+    return json.loads(buf.value.decode())
 
 
 def launch_count() -> int:

@@ -36,6 +36,17 @@ int set_error(int code, const char* fmt, ...);
 cudaStream_t current_stream();
 void count_launch(int n = 1);  // bookkeeping behind ffb_launch_count()
 
+// Optional per-kernel timing with CUDA events on the launching stream (ffb_prof_enable / ffb_prof_report).
+// `bytes` is the ALGORITHMIC HBM traffic of the launch, used for the roofline figures of bench.py.
+bool prof_on();
+void prof_push(const char* name, double bytes);
+void prof_pop();
+struct ProfScope {
+  bool on;
+  ProfScope(const char* name, double bytes) : on(prof_on()) { if (on) prof_push(name, bytes); }
+  ~ProfScope() { if (on) prof_pop(); }
+};
+
 #define FFB_CUDA(call)                                                                         \
   do {                                                                                         \
     cudaError_t _e = (call);                                                                   \

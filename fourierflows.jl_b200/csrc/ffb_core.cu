@@ -3,7 +3,10 @@
 // download `Array(x)` src/output.jl:79).
 #include <atomic>
 #include <cstring>
+#include <map>
 #include <mutex>
+#include <string>
+#include <vector>
 #include "ffb_common.cuh"
 
 namespace ffb {
@@ -24,6 +27,19 @@ int set_error(int code, const char* fmt, ...) {
 }
 
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+struct ProfRec { std::string name; cudaEvent_t a, b; double bytes; };
+static bool g_prof = false;
+static std::vector<ProfRec> g_recs;
+bool prof_on() { return g_prof; }
+void prof_push(const char* name, double bytes) {
+  ProfRec r;
+  r.name = name; r.bytes = bytes;
+  cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+  cudaEventRecord(r.a, current_stream());
+  g_recs.push_back(r);
+}
+void prof_pop() { if (!g_recs.empty()) cudaEventRecord(g_recs.back().b, current_stream()); }
 
 cudaStream_t current_stream() {
   if (!g_stream) {
@@ -99,6 +115,42 @@ int ffb_sync(void) {
 int ffb_launch_count(uint64_t* n) {
   FFB_REQUIRE(n, FFB_EINVAL, "n is NULL");
   *n = g_launches.load();
+  return FFB_OK;
+}
+
+int ffb_prof_enable(int on) {
+  for (auto& r : g_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  g_recs.clear();
+  g_prof = on != 0;
+  return FFB_OK;
+}
+
+// JSON array of {"name", "launches", "ms", "bytes"} aggregated per kernel class since ffb_prof_enable(1)
+int ffb_prof_report(char* buf, size_t len) {
+  FFB_REQUIRE(buf && len > 2, FFB_EINVAL, "bad buffer");
+  cudaStream_t st = current_stream();
+  FFB_REQUIRE(st, FFB_ECUDA, "no CUDA stream (no device?)");
+  FFB_CUDA(cudaStreamSynchronize(st));
+  struct Agg { long n = 0; double ms = 0, bytes = 0; };
+  std::map<std::string, Agg> agg;
+  for (auto& r : g_recs) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) { cudaGetLastError(); continue; }
+    Agg& a = agg[r.name];
+    a.n++; a.ms += ms; a.bytes += r.bytes;
+  }
+  std::string out = "[";
+  bool first = true;
+  for (auto& kv : agg) {
+    char line[320];
+    snprintf(line, sizeof(line), "%s{\"name\": \"%s\", \"launches\": %ld, \"ms\": %.6f, \"bytes\": %.0f}", first ? "" : ", ",
+             kv.first.c_str(), kv.second.n, kv.second.ms, kv.second.bytes);
+    out += line;
+    first = false;
+  }
+  out += "]";
+  FFB_REQUIRE(out.size() + 1 <= len, FFB_EINVAL, "report buffer too small (%zu needed)", out.size() + 1);
+  memcpy(buf, out.c_str(), out.size() + 1);
   return FFB_OK;
 }
 

@@ -191,6 +191,13 @@ static int pow2_pass(int N, int mode, int dir, const void* in, void* out, long l
   const size_t smem = pow2_smem_bytes<T>(N, p.W, mode);
   const long long gx = (nlines + p.W - 1) / p.W;
   FFB_REQUIRE(gx < (1ll << 31), FFB_EUNSUPPORTED, "too many lines for one launch");
+  static const char* mode_names[4] = {"c2c_rows", "c2c_cols", "r2c_rows", "c2r_rows"};
+  char pname[64];
+  snprintf(pname, sizeof(pname), "fft_%s_%s_N%d", mode_names[mode], sizeof(T) == 8 ? "f64" : "f32", N);
+  // algorithmic bytes: every element of the line set is read once and written once
+  const double lines = (double)nlines * (double)nouter;
+  const double in_elems = (mode == C2R_ROWS) ? N + 1 : N, out_elems = (mode == R2C_ROWS) ? N + 1 : N;
+  ProfScope ps(pname, lines * (in_elems + out_elems) * sizeof(cx<T>));
   for (long long o0 = 0; o0 < nouter; o0 += 65535) {
     const long long cnt = std::min<long long>(65535, nouter - o0);
     p.in = reinterpret_cast<const cx<T>*>(in) + o0 * in_os;

@@ -113,21 +113,24 @@ static int calcN_impl(ffb_problem* p, void* N, const void* sol, double t) {
       return ffb_ew_spectral_mul(N, p->sh1, 0.0, 1.0, p->kr, 1, nullptr, 0, nullptr, 0, nullptr, 0, 0, d);
     case FFB_CALCN_VORTICITY2D: {
       const unsigned rows = (unsigned)d->dims[1];
+      { ProfScope ps("calcN_vort_prep", 3.0 * p->sbytes + p->rbytes);
       vort_prep_kernel<T><<<rows, 256, 0, s>>>((cx<T>*)p->sh1, (cx<T>*)p->sh2, (const cx<T>*)sol, (const T*)p->invKrsq, (const T*)p->kr, (const T*)p->l, n0);
-      count_launch();
+      count_launch(); }
       FFB_CHECK_LAUNCH();
       if ((rc = ffb_fft_inverse(p->plan, p->sh1, p->ph1))) return rc;   // u
       if ((rc = ffb_fft_inverse(p->plan, p->sh2, p->ph2))) return rc;   // v
       if ((rc = ffb_fft_inverse(p->plan, sol, p->ph3))) return rc;      // zeta (zeta_h = sol; the transform preserves its input)
       const unsigned blocks = (unsigned)std::min<long long>((p->nphys + 255) / 256, (long long)num_sms() * 16);
+      { ProfScope ps("calcN_vort_products", 5.0 * p->pbytes);
       mul2_real_kernel<T><<<blocks, 256, 0, s>>>((T*)p->ph1, (T*)p->ph2, (const T*)p->ph3, p->nphys);
-      count_launch();
+      count_launch(); }
       FFB_CHECK_LAUNCH();
       if ((rc = ffb_fft_forward(p->plan, p->ph1, p->sh1))) return rc;
       if ((rc = ffb_fft_forward(p->plan, p->ph2, p->sh2))) return rc;
+      { ProfScope ps("calcN_vort_combine", 3.0 * p->sbytes);
       vort_combine_kernel<T><<<rows, 256, 0, s>>>((cx<T>*)N, (const cx<T>*)p->sh1, (const cx<T>*)p->sh2, (const T*)p->kr, (const T*)p->l, n0,
                                                   d->alias_lo[0], d->alias_hi[0], d->alias_lo[1], d->alias_hi[1]);
-      count_launch();
+      count_launch(); }
       FFB_CHECK_LAUNCH();
       return FFB_OK;
     }
@@ -135,8 +138,9 @@ static int calcN_impl(ffb_problem* p, void* N, const void* sol, double t) {
       // N = -1/2 im kr rfft(irfft(sol)^2) ; dealias!(N, grid)   (builder-defined 3-D test equation)
       if ((rc = ffb_fft_inverse(p->plan, sol, p->ph1))) return rc;
       const unsigned blocks = (unsigned)std::min<long long>((p->nphys + 255) / 256, (long long)num_sms() * 16);
+      { ProfScope ps("calcN_square", 2.0 * p->pbytes);
       square_real_kernel<T><<<blocks, 256, 0, s>>>((T*)p->ph1, p->nphys);
-      count_launch();
+      count_launch(); }
       FFB_CHECK_LAUNCH();
       if ((rc = ffb_fft_forward(p->plan, p->ph1, p->sh1))) return rc;
       return ffb_ew_spectral_mul(N, p->sh1, 0.0, -0.5, p->kr, 1, nullptr, 0, nullptr, 0, nullptr, 0, 1, d);

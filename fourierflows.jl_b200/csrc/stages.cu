@@ -66,8 +66,12 @@ template <class Op> __global__ void __launch_bounds__(256) stage_kernel(const Op
   for (; i < n; i += stride) op(i);
 }
 
-template <class Op> static int launch(const Op& op, long long n) {
+// `arrays` = number of complex state arrays read + written, `coefs` = number of coefficient operands, `filt` = filter read
+template <typename T, typename CT, int KIND, class Op>
+static int launch(const Op& op, long long n, const char* name, int arrays, int coefs, bool filt) {
   if (n <= 0) return FFB_OK;
+  const double cbytes = KIND == FFB_COEF_REAL ? sizeof(CT) : KIND == FFB_COEF_COMPLEX ? 2 * sizeof(CT) : 0;
+  ProfScope ps(name, (double)n * (arrays * 2.0 * sizeof(T) + coefs * cbytes + (filt ? sizeof(T) : 0)));
   cudaStream_t s = current_stream();
   FFB_REQUIRE(s, FFB_ECUDA, "no CUDA stream (no device?)");
   const int threads = 256;
@@ -255,7 +259,7 @@ int ffb_stage_fe(void* sol, const void* N, const ffb_coef* L, double dt, const v
   int rc = check_coef(L, "L"); if (rc) return rc;
   FFB_DISPATCH_TCK(dtype, L->dtype, L->kind, {
     OpFE<T, CT, K> op{sol, N, view<CT, K>(L), (CT)dt, filter};
-    return launch(op, n);
+    return launch<T, CT, K>(op, n, "stage_fe", 3, 1, filter != nullptr);
   });
   return FFB_OK;
 }
@@ -266,7 +270,7 @@ int ffb_stage_rk4_substep(void* sol1, void* rhs, const void* u, const void* sol,
   int rc = check_coef(L, "L"); if (rc) return rc;
   FFB_DISPATCH_TCK(dtype, L->dtype, L->kind, {
     OpRK4Sub<T, CT, K> op{sol1, rhs, u, sol, view<CT, K>(L), (CT)c};
-    return launch(op, n);
+    return launch<T, CT, K>(op, n, "stage_rk4_substep", u == sol ? 4 : 5, 1, false);
   });
   return FFB_OK;
 }
@@ -279,7 +283,7 @@ int ffb_stage_rk4_final(void* sol, const void* rhs1, const void* rhs2, const voi
   FFB_DISPATCH_TCK(dtype, L->dtype, L->kind, {
     // `dt/6` is formed in the clock's type T (src/timesteppers.jl:261)
     OpRK4Final<T, CT, K> op{sol, rhs1, rhs2, rhs3, rhs4, sol1, view<CT, K>(L), (CT)((T)dt / (T)6), filter, store_rhs4};
-    return launch(op, n);
+    return launch<T, CT, K>(op, n, "stage_rk4_final", store_rhs4 ? 8 : 7, 1, filter != nullptr);
   });
   return FFB_OK;
 }
@@ -291,7 +295,7 @@ int ffb_stage_lsrk54(void* sol, void* S2, void* rhs, const ffb_coef* L, double A
   int rc = check_coef(L, "L"); if (rc) return rc;
   FFB_DISPATCH_TCK(dtype, L->dtype, L->kind, {
     OpLSRK<T, CT, K> op{sol, S2, rhs, view<CT, K>(L), (CT)(T)A, (CT)(T)B, (CT)dt, first, filter};
-    return launch(op, n);
+    return launch<T, CT, K>(op, n, "stage_lsrk54", first ? 4 : 5, 1, filter != nullptr);
   });
   return FFB_OK;
 }
@@ -305,7 +309,7 @@ int ffb_stage_etdrk4_substep12(void* out, const ffb_coef* exphLdt, const void* s
   FFB_REQUIRE(exphLdt->kind == zeta->kind && exphLdt->dtype == zeta->dtype, FFB_EINVAL, "ETD coefficients must share kind and dtype");
   FFB_DISPATCH_TCK(dtype, zeta->dtype, zeta->kind, {
     OpETD12<T, CT, K> op{out, view<CT, K>(exphLdt), sol, view<CT, K>(zeta), N};
-    return launch(op, n);
+    return launch<T, CT, K>(op, n, "stage_etdrk4_substep12", 3, 2, false);
   });
   return FFB_OK;
 }
@@ -319,7 +323,7 @@ int ffb_stage_etdrk4_substep3(void* out, const ffb_coef* exphLdt, const void* so
   FFB_REQUIRE(exphLdt->kind == zeta->kind && exphLdt->dtype == zeta->dtype, FFB_EINVAL, "ETD coefficients must share kind and dtype");
   FFB_DISPATCH_TCK(dtype, zeta->dtype, zeta->kind, {
     OpETD3<T, CT, K> op{out, view<CT, K>(exphLdt), sol1, view<CT, K>(zeta), N1, N3};
-    return launch(op, n);
+    return launch<T, CT, K>(op, n, "stage_etdrk4_substep3", 4, 2, false);
   });
   return FFB_OK;
 }
@@ -335,7 +339,7 @@ int ffb_stage_etdrk4_update(void* sol, const ffb_coef* expLdt, const ffb_coef* a
   }
   FFB_DISPATCH_TCK(dtype, alpha->dtype, alpha->kind, {
     OpETDUpd<T, CT, K> op{sol, view<CT, K>(expLdt), view<CT, K>(alpha), view<CT, K>(beta), view<CT, K>(gamma), N1, N2, N3, N4, filter};
-    return launch(op, n);
+    return launch<T, CT, K>(op, n, "stage_etdrk4_update", 6, 4, filter != nullptr);
   });
   return FFB_OK;
 }
@@ -350,7 +354,7 @@ int ffb_stage_ab3(void* sol, void* rhs, const void* rhs_m1, const void* rhs_m2, 
   FFB_DISPATCH_TCK(dtype, L->dtype, L->kind, {
     (void)sizeof(CT);
     OpAB3<T, K> op{sol, rhs, rhs_m1, rhs_m2, view<T, K>(L), (T)dt, euler, filter};
-    return launch(op, n);
+    return launch<T, T, K>(op, n, "stage_ab3", euler ? 4 : 6, 1, filter != nullptr);
   });
   return FFB_OK;
 }

@@ -68,6 +68,11 @@ int ffb_set_stream(void* cuda_stream);          /* NULL = the library's own non-
 int ffb_get_stream(void** cuda_stream);
 int ffb_sync(void);
 int ffb_launch_count(uint64_t* n);              /* number of kernels this library has launched so far */
+/* measurement aid (no reference counterpart; SURVEY 5 "tracing / profiling: none"): brackets every kernel launch with
+ * CUDA events on the launching stream; the report is a JSON array of {"name","launches","ms","bytes"} per kernel class,
+ * `bytes` being the algorithmic HBM traffic */
+int ffb_prof_enable(int on);
+int ffb_prof_report(char* buf, size_t buflen);
 
 /* B1 array/device seam: `zeros(GPU(), T, dims)` src/utils.jl:80; `device_array(GPU())` src/utils.jl:330;
  * upload `device_array(dev){T}(host)` src/domains.jl:77; download `Array(dev_array)` src/output.jl:79. */
