@@ -90,8 +90,7 @@ static int build_tables(ffb_plan* pl) {
       for (int i = 0; i < np; ++i) {
         const int r = rad[i];
         if (Ns > 1)
-          for (int k = 1; k < r; ++k)
-            for (int a = 0; a < Ns; ++a) h.push_back(unit_root<T>((long long)a * k, (long long)Ns * r));
+          for (int a = 0; a < Ns; ++a) h.push_back(unit_root<T>((long long)a, (long long)Ns * r));
         Ns *= r;
       }
       if (h.empty()) h.push_back(mk<T>(1, 0));

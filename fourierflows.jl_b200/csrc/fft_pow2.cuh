@@ -32,7 +32,7 @@ struct Pow2Params {
   long long nlines;                  // lines per outer index
   int W;                             // lines per CTA
   T scale;                           // applied to the output when != 1 (inverse normalisation)
-  const cx<T>* tw;                   // per-pass twiddles, forward sign: for each pass with Ns > 1, [(k-1)*Ns + a]
+  const cx<T>* tw;                   // base twiddles, forward sign: for each pass with Ns > 1, exp(-2 pi i a/(Ns r)), a < Ns
   const cx<T>* twr;                  // exp(-i*pi*k/N), k < N, for the r2c / c2r split step
 };
 
@@ -95,7 +95,21 @@ template <typename T, int DIR> FFB_D cx<T> load_tw(const cx<T>* p) {
   return mk<T>(q.x, DIR < 0 ? q.y : -q.y);
 }
 
-// All passes of one line, recursively over the radix pack.  TWOFF = offset of this pass's twiddles in the table.
+// Multiply v[b + k*nb] by w1^k, k = 1..r-1, using the binary expansion of k: only w1, w1^2, w1^4, w1^8 are formed
+// (squarings), so a butterfly needs ONE table load instead of r-1 and at most log2(r) roundings per twiddle.
+template <typename T, int R, int r, int b> FFB_D void apply_twiddle_powers(cx<T> (&v)[R], cx<T> w) {
+  constexpr int nb = R / r;
+#pragma unroll
+  for (int bit = 1; bit < r; bit <<= 1) {
+#pragma unroll
+    for (int k = 1; k < r; ++k)
+      if (k & bit) v[b + k * nb] = v[b + k * nb] * w;
+    if (bit * 2 < r) w = mk<T>(w.x * w.x - w.y * w.y, (w.x + w.x) * w.y);
+  }
+}
+
+// All passes of one line, recursively over the radix pack.  TWOFF = offset of this pass's base twiddles
+// (tw[TWOFF + a] = exp(-2*pi*i*a/(Ns*r)), a < Ns) in the table.
 template <typename T, int DIR, bool COLS, int R, int N, int Ns, int TWOFF, int r, int... Rest>
 FFB_D void run_passes(cx<T> (&v)[R], int t, int w, int W, typename xword<T>::type* xb, const cx<T>* tw) {
   constexpr int Tn = N / R, nb = R / r;
@@ -103,26 +117,51 @@ FFB_D void run_passes(cx<T> (&v)[R], int t, int w, int W, typename xword<T>::typ
     constexpr int b = decltype(B)::value;
     if constexpr (Ns > 1) {
       const int a = (t + b * Tn) & (Ns - 1);
-#pragma unroll
-      for (int k = 1; k < r; ++k) v[b + k * nb] = v[b + k * nb] * load_tw<T, DIR>(tw + TWOFF + (k - 1) * Ns + a);
+      apply_twiddle_powers<T, R, r, b>(v, load_tw<T, DIR>(tw + TWOFF + a));
     }
     bfly_at<DIR, R, r, b>(v);
   });
   if constexpr (sizeof...(Rest) > 0) {
     exchange<T, COLS, R, N, Ns, r>(v, t, w, W, xb);
-    run_passes<T, DIR, COLS, R, N, Ns * r, TWOFF + (Ns > 1 ? (r - 1) * Ns : 0), Rest...>(v, t, w, W, xb, tw);
+    run_passes<T, DIR, COLS, R, N, Ns * r, TWOFF + (Ns > 1 ? Ns : 0), Rest...>(v, t, w, W, xb, tw);
   }
 }
 
+// exp(-i*pi*m/16), m = 0..15: the split-step twiddle of point k = t + m*N/16 is twr[t] times this constant
+template <typename T> struct split_consts {
+  static constexpr T c[16] = {T(1.0L), T(0.98078528040323044912618223613424L), T(0.92387953251128675612818318939679L),
+                              T(0.83146961230254523707878837761791L), T(0.70710678118654752440084436210485L),
+                              T(0.55557023301960222474283081394853L), T(0.38268343236508977172845998403040L),
+                              T(0.19509032201612826784828486847702L), T(0.0L), T(-0.19509032201612826784828486847702L),
+                              T(-0.38268343236508977172845998403040L), T(-0.55557023301960222474283081394853L),
+                              T(-0.70710678118654752440084436210485L), T(-0.83146961230254523707878837761791L),
+                              T(-0.92387953251128675612818318939679L), T(-0.98078528040323044912618223613424L)};
+};
+// twr[t + m*Tn] for the thread's 16 (or R) points; R == 16 uses one load and constants, smaller R loads the table
+template <typename T, int R, int N, int M> FFB_D cx<T> split_twiddle(const cx<T>* twr, cx<T> base, int t) {
+  constexpr int Tn = N / R;
+  if constexpr (R == 16) {
+    if constexpr (M == 0) return base;
+    else {
+      constexpr T c = split_consts<T>::c[M], s = -split_consts<T>::c[(M + 8) & 15] * ((M + 8) >= 16 ? T(-1) : T(1));
+      // exp(-i*pi*M/16) = cos(pi M/16) - i sin(pi M/16);  sin(pi M/16) = cos(pi (M-8)/16) = -cos(pi (M+8)/16)
+      return mk<T>(base.x * c - base.y * (-s), base.x * (-s) + base.y * c);
+    }
+  } else {
+    return load_tw<T, -1>(twr + t + M * Tn);
+  }
+}
+
+// Field data is touched once per pass: stream it (evict-first) so L1/L2 keep the twiddle tables.
 template <typename T> FFB_D cx<T> ldc(const cx<T>* p) {
   using V = typename vec2<T>::type;
-  V q = *reinterpret_cast<const V*>(p);
+  V q = __ldcs(reinterpret_cast<const V*>(p));
   return mk<T>(q.x, q.y);
 }
 template <typename T> FFB_D void stc(cx<T>* p, cx<T> c) {
   using V = typename vec2<T>::type;
   V q; q.x = c.x; q.y = c.y;
-  *reinterpret_cast<V*>(p) = q;
+  __stcs(reinterpret_cast<V*>(p), q);
 }
 
 template <typename T, int DIR, int MODE, int MAXT, int MINB, int R, int... Rs>
@@ -148,16 +187,17 @@ __global__ void __launch_bounds__(MAXT, MINB) fft_pow2_kernel(const Pow2Params<T
   if constexpr (MODE == C2R_ROWS) {
     // Z[k] = (X[k] + conj(X[N-k])) + i*exp(+i*pi*k/N)*(X[k] - conj(X[N-k]))
     const cx<T>* in = reinterpret_cast<const cx<T>*>(p.in) + outer * p.in_os + line * p.in_ls;
-#pragma unroll
-    for (int m = 0; m < R; ++m) {
+    const cx<T> wbase = load_tw<T, -1>(p.twr + t);
+    static_for<0, R>([&](auto M) {
+      constexpr int m = decltype(M)::value;
       const int k = t + m * Tn;
       cx<T> a = mk<T>(0, 0), b = mk<T>(0, 0);
       if (active) { a = ldc(in + k); b = ldc(in + (N - k)); }
       if (k == 0) { a.y = T(0); b.y = T(0); }  // c2r ignores Im X[0] and Im X[N] (FFTW / cuFFT / pocketfft convention)
-      const cx<T> wk = conj(load_tw<T, -1>(p.twr + k));
+      const cx<T> wk = conj(split_twiddle<T, R, N, m>(p.twr, wbase, t));
       const cx<T> s = a + conj(b), d = a - conj(b);
       v[m] = s + mul_i(wk * d);
-    }
+    });
   } else {
     const cx<T>* in = reinterpret_cast<const cx<T>*>(p.in) + outer * p.in_os + line * p.in_ls;
 #pragma unroll
@@ -181,21 +221,22 @@ __global__ void __launch_bounds__(MAXT, MINB) fft_pow2_kernel(const Pow2Params<T
     __syncthreads();
     cx<T>* out = reinterpret_cast<cx<T>*>(p.out) + outer * p.out_os + line * p.out_ls;
     const T half = T(0.5);
-#pragma unroll
-    for (int m = 0; m < R; ++m) {
+    const cx<T> wbase = load_tw<T, -1>(p.twr + t);
+    static_for<0, R>([&](auto M) {
+      constexpr int m = decltype(M)::value;
       const int k = t + m * Tn;
       const int kp = (N - k) & (N - 1);
       cx<T> zp;
       xput<T, 0>(zp, xb[addr(kp)]);
       if constexpr (PL == 2) xput<T, 1>(zp, xb[plane + addr(kp)]);
-      const cx<T> wk = load_tw<T, -1>(p.twr + k);
+      const cx<T> wk = split_twiddle<T, R, N, m>(p.twr, wbase, t);
       const cx<T> s = v[m] + conj(zp), d = v[m] - conj(zp);
       const cx<T> x = half * (s + mul_mi(wk * d));
       if (active) {
         stc(out + k, x);
         if (k == 0) stc(out + N, mk<T>(v[m].x - v[m].y, T(0)));
       }
-    }
+    });
   } else if constexpr (MODE == C2R_ROWS) {
     if (active) {
       cx<T>* out = reinterpret_cast<cx<T>*>(p.out) + outer * p.out_os + line * p.out_ls;

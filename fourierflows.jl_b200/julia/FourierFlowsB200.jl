@@ -1,0 +1,241 @@
+# FourierFlowsB200.jl -- thin Julia binding of libfourierflows_b200.so for FourierFlows.jl v0.10.7.
+#
+# NOT EXECUTABLE IN THE BUILD IMAGE (no Julia toolchain): this file is the reference-side binding a maintainer
+# would add; every `ccall` targets a symbol declared in include/fourierflows_b200.h.  It hooks the three seams of
+# SURVEY.md section 8b without touching user code:
+#   B1  `zeros(::B200, T, dims)` / `device_array(::B200)`        (src/utils.jl:79-80, 329-332)
+#   B2  `plan_flows_rfft` / `plan_flows_fft`, `mul!`, `ldiv!`     (src/domains.jl:2-5; AbstractFFTs plan protocol)
+#   B3  one `stepforward!` method per stepper on B200 arrays      (src/timesteppers.jl:111-667)
+# `dealias!`, `makefilter`, `getetdcoeffs` get B200 methods as well.  No CUDA.jl, no KernelAbstractions, no CPU fallback.
+module FourierFlowsB200
+
+using FourierFlows
+using FourierFlows: AbstractGrid, OneDGrid, TwoDGrid, ThreeDGrid, Device, Equation, fltype, cxtype
+import FourierFlows: device_array, plan_flows_fft, plan_flows_rfft, dealias!, makefilter, getetdcoeffs, getexpLs,
+                     stepforward!, supersize
+import LinearAlgebra: mul!, ldiv!
+import Base: size, zeros, copyto!, Array, \, *
+
+const lib = get(ENV, "FFB200_LIB", "libfourierflows_b200.so")
+
+struct B200 <: Device end          # `TwoDGrid(B200(); nx, Lx)` selects this backend
+
+# ---------------------------------------------------------------- status handling
+function check(rc::Cint)
+  rc == 0 && return nothing
+  msg = unsafe_string(ccall((:ffb_last_error, lib), Cstring, ()))
+  rc == -2 && throw(DomainError(msg))      # FFB_EDOMAIN  <-> src/domains.jl:66,179,316
+  rc == -3 && throw(OutOfMemoryError())
+  error("libfourierflows_b200 ($rc): $msg")
+end
+
+ffbtype(::Type{Float32}) = Cint(0); ffbtype(::Type{Float64}) = Cint(1)
+ffbtype(::Type{Complex{T}}) where T = ffbtype(T)
+
+# ---------------------------------------------------------------- B1: device arrays
+mutable struct B200Array{T,N} <: AbstractArray{T,N}
+  ptr  :: Ptr{Cvoid}
+  dims :: NTuple{N,Int}
+  function B200Array{T,N}(::UndefInitializer, dims::NTuple{N,Int}) where {T,N}
+    p = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:ffb_malloc, lib), Cint, (Ptr{Ptr{Cvoid}}, Csize_t), p, prod(dims) * sizeof(T)))
+    a = new{T,N}(p[], dims)
+    finalizer(x -> ccall((:ffb_free, lib), Cint, (Ptr{Cvoid},), x.ptr), a)   # ffb_free is thread-safe
+    return a
+  end
+end
+B200Array{T}(u::UndefInitializer, dims::Int...) where T = B200Array{T,length(dims)}(u, dims)
+size(a::B200Array) = a.dims
+supersize(a::B200Array) = size(a)                                              # src/utils.jl:57
+Base.getindex(::B200Array, i...) = error("scalar indexing of a B200Array is disallowed (cf. CUDA.allowscalar(false))")
+
+function B200Array(h::Array{T,N}) where {T,N}                                   # upload: device_array(dev){T}(host)
+  a = B200Array{T,N}(undef, size(h))
+  check(ccall((:ffb_h2d, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Csize_t), a.ptr, h, sizeof(h)))
+  check(ccall((:ffb_sync, lib), Cint, ()))
+  return a
+end
+function Array(a::B200Array{T,N}) where {T,N}                                   # download: src/output.jl:79
+  h = Array{T,N}(undef, size(a))
+  check(ccall((:ffb_d2h, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Csize_t), h, a.ptr, sizeof(h)))
+  return h
+end
+function zeros(::B200, ::Type{T}, dims) where T                                 # src/utils.jl:80
+  a = B200Array{T,length(dims)}(undef, Tuple(dims))
+  check(ccall((:ffb_memset_zero, lib), Cint, (Ptr{Cvoid}, Csize_t), a.ptr, prod(dims) * sizeof(T)))
+  return a
+end
+device_array(::B200) = B200Array
+device_array(::B200, T, dim) = B200Array{T,dim}
+copyto!(d::B200Array{T}, s::B200Array{T}) where T =
+  (check(ccall((:ffb_d2d, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Csize_t), d.ptr, s.ptr, prod(size(d)) * sizeof(T))); d)
+
+# ---------------------------------------------------------------- B2: plans (AbstractFFTs protocol as used by the reference)
+mutable struct B200Plan{T,K}    # K = :r2c | :c2c
+  handle :: Ptr{Cvoid}
+  sz     :: Tuple
+end
+function makeplan(::Type{T}, sz::Tuple, kind::Symbol) where T
+  n = Int64[sz...]
+  h = Ref{Ptr{Cvoid}}(C_NULL)
+  check(ccall((:ffb_plan_create, lib), Cint, (Ptr{Ptr{Cvoid}}, Cint, Ptr{Int64}, Cint, Cint, Cint, Cint),
+              h, length(sz), n, ffbtype(T), kind == :r2c ? 0 : 1, 1, 0))
+  p = B200Plan{T,kind}(h[], sz)
+  finalizer(x -> ccall((:ffb_plan_destroy, lib), Cint, (Ptr{Cvoid},), x.handle), p)
+  return p
+end
+# src/domains.jl:4-5 analogues (the `flags=effort` keyword is dropped exactly like for CuArrays)
+plan_flows_fft(a::B200Array{Complex{T}}, args...; flags=nothing, kw...) where T = makeplan(T, size(a), :c2c)
+plan_flows_rfft(a::B200Array{T}, args...; flags=nothing, kw...) where T<:AbstractFloat = makeplan(T, size(a), :r2c)
+
+mul!(out::B200Array, p::B200Plan, a::B200Array) =                               # src/diffusion.jl:139,171
+  (check(ccall((:ffb_fft_forward, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), p.handle, a.ptr, out.ptr)); out)
+ldiv!(out::B200Array, p::B200Plan, ah::B200Array) =                             # src/diffusion.jl:137,154-155
+  (check(ccall((:ffb_fft_inverse, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), p.handle, ah.ptr, out.ptr)); out)
+*(p::B200Plan{T,:r2c}, a::B200Array{T}) where T = mul!(B200Array{Complex{T}}(undef, (p.sz[1] ÷ 2 + 1, p.sz[2:end]...)...), p, a)
+\(p::B200Plan{T,:r2c}, ah::B200Array{Complex{T}}) where T = ldiv!(B200Array{T}(undef, p.sz...), p, ah)
+*(p::B200Plan{T,:c2c}, a::B200Array{Complex{T}}) where T = mul!(similar(a), p, a)
+\(p::B200Plan{T,:c2c}, a::B200Array{Complex{T}}) where T = ldiv!(similar(a), p, a)
+Base.similar(a::B200Array{T,N}) where {T,N} = B200Array{T,N}(undef, size(a))
+
+# ---------------------------------------------------------------- descriptors shared by the grid-side kernels
+struct FFBDesc
+  ndim :: Cint; dims :: NTuple{4,Int64}; dtype :: Cint; alias_lo :: NTuple{3,Int32}; alias_hi :: NTuple{3,Int32}
+end
+rng(r::Nothing) = (Int32(0), Int32(0)); rng(r::UnitRange) = (Int32(first(r)), Int32(last(r)))
+function desc(fh::B200Array{T}, g::AbstractGrid, kal) where T
+  nd = g isa OneDGrid ? 1 : g isa TwoDGrid ? 2 : 3
+  d = ntuple(i -> i <= nd ? Int64(size(fh, i)) : Int64(1), 3)
+  nf = Int64(prod(size(fh)[nd+1:end]))
+  al = (rng(kal), nd >= 2 ? rng(g.lalias) : rng(nothing), nd >= 3 ? rng(g.malias) : rng(nothing))
+  FFBDesc(nd, (d..., nf), ffbtype(T), map(first, al), map(last, al))
+end
+
+# `dealias!(fh, grid)` src/domains.jl:428-476 (kralias vs kalias from size(fh,1) == grid.nkr, :437,450,464)
+function dealias!(fh::B200Array, g::AbstractGrid{T,A,<:UnitRange}) where {T,A}
+  kal = size(fh, 1) == g.nkr ? g.kralias : g.kalias
+  d = Ref(desc(fh, g, kal))
+  check(ccall((:ffb_dealias, lib), Cint, (Ptr{Cvoid}, Ptr{FFBDesc}), fh.ptr, d))
+  return nothing
+end
+
+# ---------------------------------------------------------------- coefficients (`equation.L`, ETD coefficients)
+struct FFBCoef; ptr :: Ptr{Cvoid}; kind :: Cint; dtype :: Cint; re :: Cdouble; im :: Cdouble; end
+coef(L::Number, T) = FFBCoef(C_NULL, 0, ffbtype(fltype(T)), real(L), imag(L))
+coef(L::B200Array{S}, T) where S<:Real = FFBCoef(L.ptr, 1, ffbtype(S), 0.0, 0.0)
+coef(L::B200Array{Complex{S}}, T) where S = FFBCoef(L.ptr, 2, ffbtype(S), 0.0, 0.0)
+fptr(ts) = hasproperty(ts, :filter) ? ts.filter.ptr : C_NULL
+
+# ---------------------------------------------------------------- B3: one stepforward! method per stepper (reference control flow kept)
+const B200Sol = B200Array
+
+function stepforward!(sol::B200Sol{T}, clock, ts::Union{FourierFlows.ETDRK4TimeStepper,FourierFlows.FilteredETDRK4TimeStepper},
+                      eq, vars, params, grid) where T
+  n = Int64(length(sol)); dt = ffbtype(T)
+  cE, cE2, cz, ca, cb, cg = (Ref(coef(c, T)) for c in (ts.expLdt, ts.exp½Ldt, ts.ζ, ts.α, ts.β, ts.Γ))
+  eq.calcN!(ts.N₁, sol, clock.t, clock, vars, params, grid)                                    # :520
+  check(ccall((:ffb_stage_etdrk4_substep12, lib), Cint, (Ptr{Cvoid}, Ptr{FFBCoef}, Ptr{Cvoid}, Ptr{FFBCoef}, Ptr{Cvoid}, Cint, Int64),
+              ts.sol₁.ptr, cE2, sol.ptr, cz, ts.N₁.ptr, dt, n))                                  # :521
+  t2 = clock.t + clock.dt/2
+  eq.calcN!(ts.N₂, ts.sol₁, t2, clock, vars, params, grid)                                     # :525
+  check(ccall((:ffb_stage_etdrk4_substep12, lib), Cint, (Ptr{Cvoid}, Ptr{FFBCoef}, Ptr{Cvoid}, Ptr{FFBCoef}, Ptr{Cvoid}, Cint, Int64),
+              ts.sol₂.ptr, cE2, sol.ptr, cz, ts.N₂.ptr, dt, n))                                  # :526
+  eq.calcN!(ts.N₃, ts.sol₂, t2, clock, vars, params, grid)                                     # :529
+  check(ccall((:ffb_stage_etdrk4_substep3, lib), Cint, (Ptr{Cvoid}, Ptr{FFBCoef}, Ptr{Cvoid}, Ptr{FFBCoef}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Int64),
+              ts.sol₂.ptr, cE2, ts.sol₁.ptr, cz, ts.N₁.ptr, ts.N₃.ptr, dt, n))                   # :530
+  eq.calcN!(ts.N₄, ts.sol₂, clock.t + clock.dt, clock, vars, params, grid)                     # :534
+  check(ccall((:ffb_stage_etdrk4_update, lib), Cint,
+              (Ptr{Cvoid}, Ptr{FFBCoef}, Ptr{FFBCoef}, Ptr{FFBCoef}, Ptr{FFBCoef}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Int64),
+              sol.ptr, cE, ca, cb, cg, ts.N₁.ptr, ts.N₂.ptr, ts.N₃.ptr, ts.N₄.ptr, fptr(ts), dt, n))   # :541 (+ :552)
+  clock.t += clock.dt; clock.step += 1
+  return nothing
+end
+
+function stepforward!(sol::B200Sol{T}, clock, ts::Union{FourierFlows.RK4TimeStepper,FourierFlows.FilteredRK4TimeStepper},
+                      eq, vars, params, grid) where T
+  n = Int64(length(sol)); dty = ffbtype(T); L = Ref(coef(eq.L, T)); t = clock.t; dt = clock.dt
+  sub(rhs, u, c) = check(ccall((:ffb_stage_rk4_substep, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{FFBCoef}, Cdouble, Cint, Int64),
+                               ts.sol₁.ptr, rhs.ptr, u.ptr, sol.ptr, L, c, dty, n))
+  eq.calcN!(ts.RHS₁, sol, t, clock, vars, params, grid);            sub(ts.RHS₁, sol, dt/2)      # :239-243
+  eq.calcN!(ts.RHS₂, ts.sol₁, t+dt/2, clock, vars, params, grid);   sub(ts.RHS₂, ts.sol₁, dt/2)  # :244-248
+  eq.calcN!(ts.RHS₃, ts.sol₁, t+dt/2, clock, vars, params, grid);   sub(ts.RHS₃, ts.sol₁, dt)    # :249-253
+  eq.calcN!(ts.RHS₄, ts.sol₁, t+dt, clock, vars, params, grid)                                   # :254
+  check(ccall((:ffb_stage_rk4_final, lib), Cint,
+              (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{FFBCoef}, Cdouble, Ptr{Cvoid}, Cint, Cint, Int64),
+              sol.ptr, ts.RHS₁.ptr, ts.RHS₂.ptr, ts.RHS₃.ptr, ts.RHS₄.ptr, ts.sol₁.ptr, L, dt, fptr(ts), 1, dty, n))  # :255,261,279
+  clock.t += clock.dt; clock.step += 1
+  return nothing
+end
+
+function stepforward!(sol::B200Sol{T}, clock, ts::Union{FourierFlows.LSRK54TimeStepper,FourierFlows.FilteredLSRK54TimeStepper},
+                      eq, vars, params, grid) where T
+  n = Int64(length(sol)); dty = ffbtype(T); L = Ref(coef(eq.L, T)); t = clock.t; dt = clock.dt
+  for i = 1:5                                                                                      # :386-392 (`S² = 0` folded into i = 1)
+    eq.calcN!(ts.RHS, sol, t + ts.C[i] * dt, clock, vars, params, grid)
+    check(ccall((:ffb_stage_lsrk54, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{FFBCoef}, Cdouble, Cdouble, Cdouble, Cint, Ptr{Cvoid}, Cint, Int64),
+                sol.ptr, ts.S².ptr, ts.RHS.ptr, L, real(ts.A[i]), real(ts.B[i]), dt, i == 1, i == 5 ? fptr(ts) : C_NULL, dty, n))
+  end
+  clock.t += clock.dt; clock.step += 1
+  return nothing
+end
+
+function stepforward!(sol::B200Sol{T}, clock, ts::Union{FourierFlows.ForwardEulerTimeStepper,FourierFlows.FilteredForwardEulerTimeStepper},
+                      eq, vars, params, grid) where T
+  eq.calcN!(ts.N, sol, clock.t, clock, vars, params, grid)                                        # :112,143
+  L = Ref(coef(eq.L, T))
+  check(ccall((:ffb_stage_fe, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{FFBCoef}, Cdouble, Ptr{Cvoid}, Cint, Int64),
+              sol.ptr, ts.N.ptr, L, clock.dt, fptr(ts), ffbtype(T), Int64(length(sol))))          # :113,144
+  clock.t += clock.dt; clock.step += 1
+  return nothing
+end
+
+# AB3 keeps the reference's field names; the history "copies" (:647-648) become pointer swaps inside the arrays
+function stepforward!(sol::B200Sol{T}, clock, ts::Union{FourierFlows.AB3TimeStepper,FourierFlows.FilteredAB3TimeStepper},
+                      eq, vars, params, grid) where T
+  eq.calcN!(ts.RHS, sol, clock.t, clock, vars, params, grid)                                      # :639,654
+  L = Ref(coef(eq.L, T))
+  check(ccall((:ffb_stage_ab3, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{FFBCoef}, Cdouble, Int64, Ptr{Cvoid}, Cint, Int64),
+              sol.ptr, ts.RHS.ptr, ts.RHS₋₁.ptr, ts.RHS₋₂.ptr, L, clock.dt, clock.step, fptr(ts), ffbtype(T), Int64(length(sol))))
+  clock.t += clock.dt; clock.step += 1
+  ts.RHS.ptr, ts.RHS₋₁.ptr, ts.RHS₋₂.ptr = ts.RHS₋₂.ptr, ts.RHS.ptr, ts.RHS₋₁.ptr                 # RHS₋₂ ← RHS₋₁ ← RHS
+  return nothing
+end
+
+# ---------------------------------------------------------------- ETD coefficients and filter on the device
+function getetdcoeffs(dt, L::B200Array{S}; ncirc=32, rcirc=1) where S             # src/timesteppers.jl:689-721
+  (ncirc == 32 && rcirc == 1) || error("libfourierflows_b200 implements the reference's default contour (ncirc=32, rcirc=1)")
+  CT = S <: Real ? Float64 : Complex{Float64}
+  E, E2, ζ, α, β, Γ = (B200Array{CT}(undef, size(L)...) for _ in 1:6)
+  c = Ref(coef(L, S))
+  check(ccall((:ffb_etd_coeffs, lib), Cint, (Cdouble, Ptr{FFBCoef}, Cint, Cint, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cdouble}),
+              dt, c, ffbtype(S), 1, length(L), E.ptr, E2.ptr, ζ.ptr, α.ptr, β.ptr, Γ.ptr, C_NULL))
+  return ζ, α, β, Γ
+end
+
+function makefilter(g::AbstractGrid{Tg,<:B200Array}, T, sz; order=4, innerK=2/3, outerK=1, tol=1e-15) where Tg   # src/domains.jl:545-546
+  f = B200Array{T}(undef, sz...)
+  kx = sz[1] == g.nkr ? g.kr : g.k
+  d = Ref(desc(f, g, nothing))
+  lp = g isa OneDGrid ? C_NULL : g.l.ptr; mp = g isa ThreeDGrid ? g.m.ptr : C_NULL
+  dy = g isa OneDGrid ? 0.0 : g.dy;       dz = g isa ThreeDGrid ? g.dz : 0.0
+  check(ccall((:ffb_make_filter, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cdouble, Cdouble, Cdouble, Cdouble, Cdouble, Cdouble, Ptr{FFBDesc}),
+              f.ptr, kx.ptr, lp, mp, g.dx, dy, dz, order, innerK, outerK, tol, d))
+  return f
+end
+
+# ---------------------------------------------------------------- elementwise vocabulary for user calcN! (closed set; anything else errors)
+"`spectral_mul!(out, in, grid; coef=im, px=1, ...)` lowers `@. out = coef * kx^px * l^py * m^pz * w * in` [+ dealias!]"
+function spectral_mul!(out::B200Array, inp::B200Array, g; coef=1, px=0, py=0, pz=0, w=nothing, accumulate=false, dealias=false)
+  half = size(inp, 1) == g.nkr
+  kal = dealias ? (half ? g.kralias : g.kalias) : nothing
+  d = Ref(desc(inp, g, kal))
+  lp = g isa OneDGrid ? C_NULL : g.l.ptr; mp = g isa ThreeDGrid ? g.m.ptr : C_NULL
+  check(ccall((:ffb_ew_spectral_mul, lib), Cint,
+              (Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cdouble, Ptr{Cvoid}, Cint, Ptr{Cvoid}, Cint, Ptr{Cvoid}, Cint, Ptr{Cvoid}, Cint, Cint, Ptr{FFBDesc}),
+              out.ptr, inp.ptr, real(coef), imag(coef), (half ? g.kr : g.k).ptr, px, lp, py, mp, pz, w === nothing ? C_NULL : w.ptr, accumulate, dealias && kal !== nothing, d))
+  return out
+end
+Base.Broadcast.BroadcastStyle(::Type{<:B200Array}) =
+  error("generic broadcasting on B200Array is not supported: use spectral_mul!, axpby!, mul_real! (no CPU fallback)")
+
+end # module
