@@ -19,5 +19,6 @@ from .utils import axpby, mul_real, parsevalsum, parsevalsum2, spectral_mul
 from . import diffusion as Diffusion
 from .equations import Burgers3D, TwoDNavierStokes
 from .cproblem import CProblem
+from .dist import Dist, DistPlan, exchange_bytes_per_rank, local_alias_range, physical_slab, slab_range, spectral_slab
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -51,7 +51,7 @@ class ffb_problem_config(C.Structure):
                 ("filter_order", C.c_double), ("filter_innerK", C.c_double), ("filter_outerK", C.c_double),
                 ("filter_tol", C.c_double), ("dt", C.c_double), ("calcN", C.c_int), ("callback", CALCN_FN),
                 ("user", C.c_void_p), ("nu", C.c_double), ("scalar_zero_L", C.c_int), ("kappa", C.c_void_p),
-                ("coef_dtype", C.c_int), ("fused", C.c_int)]
+                ("coef_dtype", C.c_int), ("fused", C.c_int), ("dist", C.c_void_p)]
 
 
 # name -> argtypes; every function returns int except the two listed in _SPECIAL
@@ -82,6 +82,12 @@ SIGNATURES = {
     "ffb_plan_describe": [_vp, C.c_char_p, _sz],
     "ffb_fft_forward": [_vp, _vp, _vp],
     "ffb_fft_inverse": [_vp, _vp, _vp],
+    "ffb_dist_unique_id": [_vp],
+    "ffb_dist_init": [_P(_vp), _i, _i, _vp],
+    "ffb_dist_destroy": [_vp],
+    "ffb_dist_info": [_vp, _P(_i), _P(_i)],
+    "ffb_dist_alltoall": [_vp, _vp, _vp, _sz],
+    "ffb_plan_create_dist": [_P(_vp), _i, _P(_i64), _i, _vp, _i],
     "ffb_wavenumbers": [_vp, _i64, _d, _i, _i],
     "ffb_ksq": [_vp, _vp, _vp, _vp, _vp, _P(ffb_desc)],
     "ffb_dealias": [_vp, _P(ffb_desc)],

@@ -16,13 +16,20 @@ _CALCN = {"zero": L.FFB_CALCN_ZERO, "diffusion": L.FFB_CALCN_DIFFUSION, "vortici
 
 class CProblem:
     def __init__(self, n, Lext, stepper="ETDRK4", dt=1e-3, calcN="vorticity2d", nu=0.0, T=np.float64, aliased_fraction=1 / 3,
-                 coef_dtype=None, kappa: DevArray = None, scalar_zero_L=False, callback=None, filter_kwargs=None, fused=0):
+                 coef_dtype=None, kappa: DevArray = None, scalar_zero_L=False, callback=None, filter_kwargs=None, fused=0, dist=None):
         n = tuple(int(v) for v in (n if isinstance(n, (tuple, list)) else (n,)))
         Lext = tuple(float(v) for v in (Lext if isinstance(Lext, (tuple, list)) else (Lext,) * len(n)))
         self.T = np.dtype(T)
         self.n = n
         self.nkr = n[0] // 2 + 1
-        self.spectral_shape = (self.nkr,) + n[1:]
+        self.dist = dist
+        P = dist.nranks if dist is not None else 1
+        if dist is not None:
+            self.spectral_shape = (self.nkr, n[1] // P, n[2])     # y-slab
+            self.physical_shape = (n[0], n[1], n[2] // P)         # z-slab
+        else:
+            self.spectral_shape = (self.nkr,) + n[1:]
+            self.physical_shape = n
         cfg = L.ffb_problem_config()
         cfg.ndim = len(n)
         cfg.n = (C.c_int64 * 3)(*n, *([1] * (3 - len(n))))
@@ -47,6 +54,7 @@ class CProblem:
         cfg.kappa = kappa.ptr if kappa is not None else None
         cfg.coef_dtype = ffb_dtype(np.float64 if coef_dtype is None else coef_dtype)
         cfg.fused = int(fused)
+        cfg.dist = dist._h if dist is not None else None
         h = C.c_void_p()
         L.call("ffb_problem_create", C.byref(h), C.byref(cfg))
         self._h = h
@@ -67,12 +75,12 @@ class CProblem:
 
     def set_physical(self, field):
         f = np.asfortranarray(field, dtype=self.T)
-        assert f.shape == self.n
+        assert f.shape == self.physical_shape
         L.call("ffb_problem_set_physical", self._h, f.ctypes.data)
         L.call("ffb_sync")
 
     def get_physical(self):
-        out = np.empty(self.n, dtype=self.T, order="F")
+        out = np.empty(self.physical_shape, dtype=self.T, order="F")
         L.call("ffb_problem_get_physical", self._h, out.ctypes.data)
         return out
 

@@ -8,6 +8,7 @@
 #include "fft_generic.cuh"
 #include "fft_pow2.cuh"
 #include "fft_pow2_dispatch.h"
+#include "dist.h"
 
 namespace ffb {
 
@@ -69,6 +70,9 @@ struct ffb_plan {
   void* ws[3];        // scratch, allocated on first use
   size_t ws_bytes;    // size of each scratch array
   std::string desc;
+  ffb_dist* dist;     // non-NULL: slab-decomposed 3-D r2c plan (physical z-slabs <-> spectral y-slabs)
+  long long nyl, nzl; // local extents: spectral (nkr, nyl, nz), physical (nx, ny, nzl)
+  int nchunks;        // exchange chunks along the local z range (overlap of all-to-all and local passes)
 };
 
 namespace ffb {
@@ -173,11 +177,17 @@ static int choose_w(int N, int mode, long long nlines) {
 }
 
 // One register-resident pass over `nouter` outer blocks (gridDim.y chunks of <= 65535).
+struct SegStride { int seg = 0; long long stride = 0; };  // seg = 0: unsegmented
+
 template <typename T>
 static int pow2_pass(int N, int mode, int dir, const void* in, void* out, long long in_es, long long in_ls, long long in_os,
                      long long out_es, long long out_ls, long long out_os, long long nlines, long long nouter, T scale,
-                     const DimTables<T>* tb, cudaStream_t st) {
+                     const DimTables<T>* tb, cudaStream_t st, SegStride in_seg = SegStride(), SegStride out_seg = SegStride()) {
   Pow2Params<T> p;
+  p.in_seg_mask = in_seg.seg ? in_seg.seg - 1 : 0x7fffffff; p.in_seg_shift = in_seg.seg ? ilog2((uint64_t)in_seg.seg) : 31;
+  p.in_seg_stride = in_seg.stride;
+  p.out_seg_mask = out_seg.seg ? out_seg.seg - 1 : 0x7fffffff; p.out_seg_shift = out_seg.seg ? ilog2((uint64_t)out_seg.seg) : 31;
+  p.out_seg_stride = out_seg.stride;
   p.in_es = in_es; p.in_ls = in_ls; p.in_os = in_os;
   p.out_es = out_es; p.out_ls = out_ls; p.out_os = out_os;
   p.nlines = nlines;
@@ -314,6 +324,75 @@ static int exec(ffb_plan* pl, const void* in, void* out, int dir) {
   return generic_fft_axis<T>(z, reinterpret_cast<cx<T>*>(out), tA, tB, 1, N0, rows, +1, inv, tb0->wN, st);
 }
 
+// ---------------------------------------------------------------- slab-decomposed 3-D r2c / c2r
+// forward : x r2c + y c2c on the local z-slab, y-pass output written in destination-rank-major order (segmented stride,
+//           no pack kernel) -> all-to-all over NCCL, chunked along z so chunk c's exchange overlaps chunk c+1's y-pass
+//           -> z c2c on the local y-slab.   inverse: mirrored (z, exchange, y, x c2r with 1/(nx ny nz)).
+template <typename T>
+static int exec_dist(ffb_plan* pl, const void* in, void* out, int dir) {
+  cudaStream_t st = current_stream();
+  FFB_REQUIRE(st, FFB_ECUDA, "no CUDA stream (no device?)");
+  ffb_dist* d = pl->dist;
+  const int P = d->nranks;
+  auto* tb0 = reinterpret_cast<DimTables<T>*>(pl->tables[0]);
+  auto* tb1 = reinterpret_cast<DimTables<T>*>(pl->tables[1]);
+  auto* tb2 = reinterpret_cast<DimTables<T>*>(pl->tables[2]);
+  const long long nkr = pl->nc[0], ny = pl->n[1], nz = pl->n[2], nyl = pl->nyl, nzl = pl->nzl;
+  const int N0 = tb0->N;
+  const long long blk = nkr * nyl * nzl;         // complex elements exchanged with each peer
+  const int nch = pl->nchunks;
+  const long long zc = nzl / nch, sub = nkr * nyl * zc;
+  int rc = ensure_ws(pl, 3);
+  if (rc) return rc;
+  cx<T>* w0 = reinterpret_cast<cx<T>*>(pl->ws[0]);
+  cx<T>* w1 = reinterpret_cast<cx<T>*>(pl->ws[1]);
+  cx<T>* w2 = reinterpret_cast<cx<T>*>(pl->ws[2]);
+  long double tot = (long double)pl->n[0] * ny * nz;
+  const T inv = (T)(1.0L / tot);
+  SegStride seg; seg.seg = (int)nyl; seg.stride = blk;
+  if (dir < 0) {
+    cx<T>* spec = reinterpret_cast<cx<T>*>(out);
+    // x: real (nx, ny, nzl) -> w0 (nkr, ny, nzl)
+    if ((rc = pow2_pass<T>(N0, R2C_ROWS, -1, in, w0, 1, N0, 0, 1, nkr, 0, ny * nzl, 1, T(1), tb0, st))) return rc;
+    for (int c = 0; c < nch; ++c) {
+      // y on z-chunk c: w0 -> w1 laid out [peer][kx, y_local, z_local]
+      if ((rc = pow2_pass<T>((int)ny, C2C_COLS, -1, w0 + c * zc * nkr * ny, w1 + c * sub, nkr, 1, nkr * ny, nkr, 1, nkr * nyl, nkr, zc, T(1), tb1,
+                             st, SegStride(), seg))) return rc;
+      cudaEvent_t e = dist_next_event(d);
+      FFB_CUDA(cudaEventRecord(e, st));
+      FFB_CUDA(cudaStreamWaitEvent(d->comm_stream, e, 0));
+      { ProfScope ps("nccl_alltoall", 0);
+      if ((rc = dist_alltoall_bytes(d, w1 + c * sub, spec + c * sub, (size_t)sub * sizeof(cx<T>), (size_t)blk * sizeof(cx<T>), d->comm_stream))) return rc; }
+    }
+    cudaEvent_t e = dist_next_event(d);
+    FFB_CUDA(cudaEventRecord(e, d->comm_stream));
+    FFB_CUDA(cudaStreamWaitEvent(st, e, 0));
+    // z on the local y-slab, in place: (nkr*nyl) columns of length nz
+    return pow2_pass<T>((int)nz, C2C_COLS, -1, spec, spec, nkr * nyl, 1, 0, nkr * nyl, 1, 0, nkr * nyl, 1, T(1), tb2, st);
+  }
+  // inverse
+  const cx<T>* spec = reinterpret_cast<const cx<T>*>(in);
+  if ((rc = pow2_pass<T>((int)nz, C2C_COLS, +1, spec, w0, nkr * nyl, 1, 0, nkr * nyl, 1, 0, nkr * nyl, 1, T(1), tb2, st))) return rc;
+  cudaEvent_t e0 = dist_next_event(d);
+  FFB_CUDA(cudaEventRecord(e0, st));
+  FFB_CUDA(cudaStreamWaitEvent(d->comm_stream, e0, 0));
+  for (int c = 0; c < nch; ++c) {
+    { ProfScope ps("nccl_alltoall", 0);
+    if ((rc = dist_alltoall_bytes(d, w0 + c * sub, w1 + c * sub, (size_t)sub * sizeof(cx<T>), (size_t)blk * sizeof(cx<T>), d->comm_stream))) return rc; }
+    cudaEvent_t e = dist_next_event(d);
+    FFB_CUDA(cudaEventRecord(e, d->comm_stream));
+    FFB_CUDA(cudaStreamWaitEvent(st, e, 0));
+    // y on z-chunk c: w1 [peer][kx, y_local, z_local] -> w2 (nkr, ny, zc)
+    if ((rc = pow2_pass<T>((int)ny, C2C_COLS, +1, w1 + c * sub, w2 + c * zc * nkr * ny, nkr, 1, nkr * nyl, nkr, 1, nkr * ny, nkr, zc, T(1), tb1, st,
+                           seg, SegStride()))) return rc;
+    // x c2r on z-chunk c
+    if ((rc = pow2_pass<T>(N0, C2R_ROWS, +1, w2 + c * zc * nkr * ny, reinterpret_cast<cx<T>*>(out) + c * zc * (long long)N0 * ny, 1, nkr, 0, 1, N0, 0,
+                           ny * zc, 1, inv, tb0, st))) return rc;
+  }
+  // the next call may overwrite w0 / w1 on the compute stream: all exchanges above have been waited for already
+  return FFB_OK;
+}
+
 }  // namespace ffb
 
 extern "C" {
@@ -335,12 +414,38 @@ int ffb_plan_create(ffb_plan** out, int ndim, const int64_t* n, int dtype, int k
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return set_error(FFB_ECUDA, "no CUDA device"); }
   auto* pl = new ffb_plan();
   pl->ndim = ndim; pl->dtype = dtype; pl->kind = kind; pl->nbatch = nbatch; pl->flags = flags;
+  pl->dist = nullptr; pl->nyl = pl->nzl = 0; pl->nchunks = 1;
   for (int d = 0; d < 3; ++d) { pl->n[d] = d < ndim ? n[d] : 1; pl->nc[d] = pl->n[d]; pl->tables[d] = nullptr; pl->ws[d] = nullptr; }
   if (kind == FFB_R2C) pl->nc[0] = pl->n[0] / 2 + 1;
   pl->ws_bytes = (size_t)pl->nc[0] * pl->nc[1] * pl->nc[2] * nbatch * 2 * dtype_size(dtype);
   int rc = dtype == FFB_F64 ? build_tables<double>(pl) : build_tables<float>(pl);
   if (rc) { ffb_plan_destroy(pl); return rc; }
   *out = pl;
+  return FFB_OK;
+}
+
+int ffb_plan_create_dist(ffb_plan** out, int ndim, const int64_t* n, int dtype, ffb_dist* dist, int nchunks) {
+  FFB_REQUIRE(dist, FFB_EINVAL, "dist is NULL");
+  FFB_REQUIRE(ndim == 3, FFB_EUNSUPPORTED, "slab decomposition is implemented for 3-D r2c grids");
+  const int P = dist->nranks;
+  FFB_REQUIRE(n[1] % P == 0 && n[2] % P == 0, FFB_EUNSUPPORTED, "ny and nz must be divisible by the number of ranks (%d)", P);
+  int rc = ffb_plan_create(out, ndim, n, dtype, FFB_R2C, 1, FFB_PLAN_DEFAULT);
+  if (rc) return rc;
+  ffb_plan* pl = *out;
+  for (int d = 0; d < 3; ++d) {
+    const bool ok = dtype == FFB_F64 ? reinterpret_cast<DimTables<double>*>(pl->tables[d])->pow2 : reinterpret_cast<DimTables<float>*>(pl->tables[d])->pow2;
+    if (!ok) { ffb_plan_destroy(pl); *out = nullptr; return set_error(FFB_EUNSUPPORTED, "slab-decomposed plans need power-of-two sizes within the register-kernel range"); }
+  }
+  pl->dist = dist;
+  pl->nyl = n[1] / P; pl->nzl = n[2] / P;
+  if (!is_pow2((uint64_t)pl->nyl)) { ffb_plan_destroy(pl); *out = nullptr; return set_error(FFB_EUNSUPPORTED, "ny / nranks must be a power of two"); }
+  int nch = nchunks > 0 ? nchunks : 4;
+  while (nch > 1 && (pl->nzl % nch != 0)) nch /= 2;
+  pl->nchunks = nch;
+  pl->ws_bytes = (size_t)pl->nc[0] * pl->n[1] * pl->nzl * 2 * dtype_size(dtype);
+  char buf[96];
+  snprintf(buf, sizeof(buf), "slab[rank %d/%d, chunks %d] ", dist->rank, P, nch);
+  pl->desc += buf;
   return FFB_OK;
 }
 
@@ -369,12 +474,14 @@ int ffb_plan_describe(const ffb_plan* pl, char* buf, size_t buflen) {
 int ffb_fft_forward(ffb_plan* pl, const void* in, void* out) {
   FFB_REQUIRE(pl && in && out, FFB_EINVAL, "NULL argument");
   if (pl->kind == FFB_R2C) FFB_REQUIRE(in != out, FFB_EINVAL, "r2c transforms are out of place");
+  if (pl->dist) return pl->dtype == FFB_F64 ? exec_dist<double>(pl, in, out, -1) : exec_dist<float>(pl, in, out, -1);
   return pl->dtype == FFB_F64 ? exec<double>(pl, in, out, -1) : exec<float>(pl, in, out, -1);
 }
 
 int ffb_fft_inverse(ffb_plan* pl, const void* in, void* out) {
   FFB_REQUIRE(pl && in && out, FFB_EINVAL, "NULL argument");
   if (pl->kind == FFB_R2C) FFB_REQUIRE(in != out, FFB_EINVAL, "c2r transforms are out of place");
+  if (pl->dist) return pl->dtype == FFB_F64 ? exec_dist<double>(pl, in, out, +1) : exec_dist<float>(pl, in, out, +1);
   return pl->dtype == FFB_F64 ? exec<double>(pl, in, out, +1) : exec<float>(pl, in, out, +1);
 }
 

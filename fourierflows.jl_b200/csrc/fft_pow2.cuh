@@ -29,6 +29,10 @@ struct Pow2Params {
   void* out;
   long long in_es, in_ls, in_os;     // element / line / outer strides of the input, in complex elements
   long long out_es, out_ls, out_os;  // same for the output
+  // Segmented element stride (slab-decomposed transforms): element i lives at (i & seg_mask)*es + (i >> seg_shift)*seg_stride,
+  // so a pass can read / write destination-rank-major blocks without a pack kernel.  Unsegmented: mask = ~0, shift = 31.
+  int in_seg_mask, in_seg_shift, out_seg_mask, out_seg_shift;
+  long long in_seg_stride, out_seg_stride;
   long long nlines;                  // lines per outer index
   int W;                             // lines per CTA
   T scale;                           // applied to the output when != 1 (inverse normalisation)
@@ -201,7 +205,10 @@ __global__ void __launch_bounds__(MAXT, MINB) fft_pow2_kernel(const Pow2Params<T
   } else {
     const cx<T>* in = reinterpret_cast<const cx<T>*>(p.in) + outer * p.in_os + line * p.in_ls;
 #pragma unroll
-    for (int m = 0; m < R; ++m) v[m] = active ? ldc(in + (long long)(t + m * Tn) * p.in_es) : mk<T>(0, 0);
+    for (int m = 0; m < R; ++m) {
+      const int i = t + m * Tn;
+      v[m] = active ? ldc(in + (long long)(i & p.in_seg_mask) * p.in_es + (long long)(i >> p.in_seg_shift) * p.in_seg_stride) : mk<T>(0, 0);
+    }
   }
   // ---------------- transform ----------------
   run_passes<T, DIR, COLS, R, N, 1, 0, Rs...>(v, t, w, W, xb, p.tw);
@@ -248,12 +255,13 @@ __global__ void __launch_bounds__(MAXT, MINB) fft_pow2_kernel(const Pow2Params<T
     if (active) {
       cx<T>* out = reinterpret_cast<cx<T>*>(p.out) + outer * p.out_os + line * p.out_ls;
       const T sc = p.scale;
+      auto off = [&](int i) { return (long long)(i & p.out_seg_mask) * p.out_es + (long long)(i >> p.out_seg_shift) * p.out_seg_stride; };
       if (sc != T(1)) {
 #pragma unroll
-        for (int m = 0; m < R; ++m) stc(out + (long long)(t + m * Tn) * p.out_es, sc * v[m]);
+        for (int m = 0; m < R; ++m) stc(out + off(t + m * Tn), sc * v[m]);
       } else {
 #pragma unroll
-        for (int m = 0; m < R; ++m) stc(out + (long long)(t + m * Tn) * p.out_es, v[m]);
+        for (int m = 0; m < R; ++m) stc(out + off(t + m * Tn), v[m]);
       }
     }
   }

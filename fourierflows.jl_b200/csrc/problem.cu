@@ -6,6 +6,7 @@
 #include <cstring>
 #include <vector>
 #include "ffb_common.cuh"
+#include "dist.h"
 
 namespace ffb {
 
@@ -255,12 +256,22 @@ int ffb_problem_create(ffb_problem** out, const ffb_problem_config* cfg) {
   const size_t es = dtype_size(cfg->dtype);
   for (int d = 0; d < 3; ++d) p->n[d] = d < cfg->ndim ? cfg->n[d] : 1;
   p->nkr = p->n[0] / 2 + 1;
-  p->nspec = p->nkr * p->n[1] * p->n[2];
-  p->nphys = p->n[0] * p->n[1] * p->n[2];
+  // slab decomposition: spectral (nkr, ny/P, nz), physical (nx, ny, nz/P)
+  const int P = cfg->dist ? cfg->dist->nranks : 1, rank = cfg->dist ? cfg->dist->rank : 0;
+  if (cfg->dist) {
+    if (cfg->ndim != 3 || !(cfg->calcN == FFB_CALCN_BURGERS3D || cfg->calcN == FFB_CALCN_ZERO || cfg->calcN == FFB_CALCN_CALLBACK)) {
+      delete p;
+      return set_error(FFB_EUNSUPPORTED, "slab-decomposed problems: 3-D grids with the Burgers / zero / callback calcN");
+    }
+    if (p->n[1] % P || p->n[2] % P) { delete p; return set_error(FFB_EUNSUPPORTED, "ny and nz must be divisible by the number of ranks"); }
+  }
+  const long long nyl = p->n[1] / (cfg->dist ? P : 1), nzl = p->n[2] / (cfg->dist ? P : 1);
+  p->nspec = p->nkr * nyl * p->n[2];
+  p->nphys = p->n[0] * p->n[1] * nzl;
   p->sbytes = (size_t)p->nspec * 2 * es; p->pbytes = (size_t)p->nphys * es; p->rbytes = (size_t)p->nspec * es;
   ffb_desc& D = p->desc;
   D.ndim = p->nd; D.dtype = p->dtype;
-  D.dims[0] = p->nkr; D.dims[1] = p->n[1]; D.dims[2] = p->n[2]; D.dims[3] = 1;
+  D.dims[0] = p->nkr; D.dims[1] = nyl; D.dims[2] = p->n[2]; D.dims[3] = 1;
   // getaliasedwavenumbers (src/domains.jl:408-421), evaluated in Float64
   for (int d = 0; d < 3; ++d) { D.alias_lo[d] = 0; D.alias_hi[d] = 0; }
   if (cfg->aliased_fraction > 0) {
@@ -270,13 +281,24 @@ int ffb_problem_create(ffb_problem** out, const ffb_problem_config* cfg) {
       D.alias_hi[d] = d == 0 ? (int32_t)p->nkr : (int32_t)std::ceil(Rf * (double)p->n[d]);  // kralias = iL:nkr for the half spectrum
     }
   }
+  if (cfg->dist && D.alias_lo[1] > 0) {
+    // lalias intersected with this rank's y-slab [rank*nyl + 1, (rank+1)*nyl], shifted to local 1-based indices
+    const long long lo = std::max<long long>(D.alias_lo[1], rank * nyl + 1), hi = std::min<long long>(D.alias_hi[1], (rank + 1) * nyl);
+    if (lo > hi) { D.alias_lo[1] = 0; D.alias_hi[1] = 0; }
+    else { D.alias_lo[1] = (int32_t)(lo - rank * nyl); D.alias_hi[1] = (int32_t)(hi - rank * nyl); }
+  }
 #define FFB_TRY(x) do { int _rc = (x); if (_rc) { ffb_problem_destroy(p); return _rc; } } while (0)
-  FFB_TRY(ffb_plan_create(&p->plan, p->nd, cfg->n, p->dtype, FFB_R2C, 1, FFB_PLAN_DEFAULT));
+  if (cfg->dist) FFB_TRY(ffb_plan_create_dist(&p->plan, p->nd, cfg->n, p->dtype, cfg->dist, 0));
+  else FFB_TRY(ffb_plan_create(&p->plan, p->nd, cfg->n, p->dtype, FFB_R2C, 1, FFB_PLAN_DEFAULT));
   // wavenumbers and Krsq / invKrsq
   p->l = p->m = nullptr;
   FFB_TRY(dalloc(p, &p->kr, (size_t)p->nkr * es, false));
   FFB_TRY(ffb_wavenumbers(p->kr, p->n[0], cfg->L[0], p->dtype, 1));
-  if (p->nd >= 2) { FFB_TRY(dalloc(p, &p->l, (size_t)p->n[1] * es, false)); FFB_TRY(ffb_wavenumbers(p->l, p->n[1], cfg->L[1], p->dtype, 0)); }
+  if (p->nd >= 2) {
+    FFB_TRY(dalloc(p, &p->l, (size_t)p->n[1] * es, false));
+    FFB_TRY(ffb_wavenumbers(p->l, p->n[1], cfg->L[1], p->dtype, 0));
+    if (cfg->dist) p->l = reinterpret_cast<char*>(p->l) + (size_t)rank * nyl * es;   // this rank's slice of the y-wavenumbers
+  }
   if (p->nd >= 3) { FFB_TRY(dalloc(p, &p->m, (size_t)p->n[2] * es, false)); FFB_TRY(ffb_wavenumbers(p->m, p->n[2], cfg->L[2], p->dtype, 0)); }
   p->Krsq = p->invKrsq = p->Ldense = p->filter = nullptr;
   const bool need_inv = cfg->calcN == FFB_CALCN_VORTICITY2D;

@@ -41,7 +41,7 @@ __global__ void ksq_kernel(T* ksq, T* inv, const T* kx, const T* l, const T* m, 
     if (ndim >= 3) v = v + mv * mv;
     const long long idx = row * n0 + i;
     if (ksq) ksq[idx] = v;
-    if (inv) inv[idx] = (idx == 0) ? T(0) : T(1) / v;
+    if (inv) inv[idx] = (v == T(0)) ? T(0) : T(1) / v;  // `invKsq[1,1,1] = 0`: the origin is the only zero of Ksq (also true on a slab)
   }
 }
 

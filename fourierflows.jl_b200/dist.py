@@ -1,0 +1,131 @@
+"""Multi-GPU slab decomposition: host-side logic.  One process per GPU; `torch.distributed` (or any other
+launcher) only moves the 128-byte NCCL unique id between ranks -- the exchange itself is NCCL inside the library.
+
+Partitioning of a 3-D grid over P ranks:
+  physical (nx, ny, nz)      -> rank r holds z in [r*nz/P, (r+1)*nz/P)          shape (nx, ny, nz/P)
+  spectral (nx/2+1, ny, nz)  -> rank r holds y (l) in [r*ny/P, (r+1)*ny/P)      shape (nx/2+1, ny/P, nz)
+Stages, dealias and filter are pointwise in spectral space (no communication); only the FFT exchanges data.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from .array import DevArray, cxtype, ffb_dtype
+
+
+def slab_range(n: int, nranks: int, rank: int):
+    """0-based half-open index range of `rank`'s slab along a dimension of extent n (n % nranks == 0)."""
+    if n % nranks != 0:
+        raise L.FFBError(L.FFB_EUNSUPPORTED, f"extent {n} is not divisible by the number of ranks {nranks}")
+    w = n // nranks
+    return rank * w, (rank + 1) * w
+
+
+def local_alias_range(alias, n: int, nranks: int, rank: int):
+    """Intersection of a 1-based inclusive alias range (`grid.lalias`) with this rank's slab, in local 1-based
+    indices; None when the slab holds no aliased index."""
+    if alias is None:
+        return None
+    lo0, hi0 = slab_range(n, nranks, rank)
+    lo, hi = max(alias[0], lo0 + 1), min(alias[1], hi0)
+    if lo > hi:
+        return None
+    return lo - lo0, hi - lo0
+
+
+def physical_slab(a: np.ndarray, nranks: int, rank: int) -> np.ndarray:
+    lo, hi = slab_range(a.shape[-1], nranks, rank)
+    return np.asfortranarray(a[..., lo:hi])
+
+
+def spectral_slab(ah: np.ndarray, nranks: int, rank: int) -> np.ndarray:
+    lo, hi = slab_range(ah.shape[1], nranks, rank)
+    return np.asfortranarray(ah[:, lo:hi, ...])
+
+
+def exchange_bytes_per_rank(shape, nranks: int, itemsize: int) -> int:
+    """Bytes each rank sends per 3-D transform: S/P * (P-1)/P."""
+    nkr = shape[0] // 2 + 1
+    S = nkr * shape[1] * shape[2] * 2 * itemsize
+    return S // nranks * (nranks - 1) // nranks
+
+
+class Dist:
+    """NCCL communicator handle (`ffb_dist`)."""
+
+    def __init__(self, rank: int, nranks: int, unique_id: bytes):
+        assert len(unique_id) == 128
+        self.rank, self.nranks = rank, nranks
+        buf = C.create_string_buffer(unique_id, 128)
+        h = C.c_void_p()
+        L.call("ffb_dist_init", C.byref(h), rank, nranks, buf)
+        self._h = h
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        L.call("ffb_dist_unique_id", buf)
+        return buf.raw
+
+    @classmethod
+    def from_torch(cls):
+        """Build the communicator inside an initialised `torch.distributed` process group (torchrun)."""
+        import torch.distributed as dist
+        rank, world = dist.get_rank(), dist.get_world_size()
+        obj = [cls.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0)
+        return cls(rank, world, obj[0])
+
+    def alltoall(self, send: DevArray, recv: DevArray):
+        L.call("ffb_dist_alltoall", self._h, send.ptr, recv.ptr, send.nbytes // self.nranks)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            L.load().ffb_dist_destroy(self._h)
+            self._h = None
+
+
+class DistPlan:
+    """Slab-decomposed `rfftplan` of a 3-D grid: `mul(out, a)` / `ldiv(out, ah)` on the local slabs."""
+
+    def __init__(self, shape, T, dist: Dist, nchunks: int = 0):
+        self.shape = tuple(int(s) for s in shape)
+        self.T = np.dtype(T)
+        self.dist = dist
+        n = (C.c_int64 * 3)(*self.shape)
+        h = C.c_void_p()
+        L.call("ffb_plan_create_dist", C.byref(h), 3, n, ffb_dtype(self.T), dist._h, nchunks)
+        self._h = h
+        P = dist.nranks
+        self.physical_shape = (self.shape[0], self.shape[1], self.shape[2] // P)
+        self.spectral_shape = (self.shape[0] // 2 + 1, self.shape[1] // P, self.shape[2])
+
+    def describe(self):
+        buf = C.create_string_buffer(512)
+        L.call("ffb_plan_describe", self._h, buf, 512)
+        return buf.value.decode()
+
+    def mul(self, out: DevArray, a: DevArray):
+        L.call("ffb_fft_forward", self._h, a.ptr, out.ptr)
+        return out
+
+    def ldiv(self, out: DevArray, ah: DevArray):
+        L.call("ffb_fft_inverse", self._h, ah.ptr, out.ptr)
+        return out
+
+    def __mul__(self, a):
+        return self.mul(DevArray(self.spectral_shape, cxtype(self.T)), a)
+
+    def solve(self, ah):
+        return self.ldiv(DevArray(self.physical_shape, self.T), ah)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                L.load().ffb_plan_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass

@@ -58,6 +58,7 @@ typedef struct {
 
 typedef struct ffb_plan ffb_plan;
 typedef struct ffb_problem ffb_problem;
+typedef struct ffb_dist ffb_dist;
 
 /* ---------------------------------------------------------------- runtime */
 const char* ffb_last_error(void);
@@ -105,6 +106,19 @@ int ffb_fft_forward(ffb_plan* plan, const void* in, void* out);
 /* `ldiv!(out, plan, in)` (src/diffusion.jl:137,154-155): inverse scaled by 1/(nx*ny*nz); `in` is preserved
  * (the reference allows c2r to destroy it; preserving is a superset). */
 int ffb_fft_inverse(ffb_plan* plan, const void* in, void* out);
+
+/* ---------------------------------------------------------------- multi-GPU slab decomposition
+ * No reference counterpart: FourierFlows.jl is single-device (README.md:58, docs/src/gpu.md:57); this is the new
+ * capability named by BASELINE.json north_star.  One process per GPU; the caller (torch.distributed, MPI, ...) moves the
+ * 128-byte NCCL unique id from rank 0 to the other ranks.  Physical arrays are split along z: rank r holds
+ * (nx, ny, nz/P); spectral arrays along y: rank r holds (nx/2+1, ny/P, nz).  ffb_fft_forward / ffb_fft_inverse on a
+ * distributed plan perform the local passes plus one NCCL all-to-all, overlapped chunk by chunk. */
+int ffb_dist_unique_id(void* host_id128);
+int ffb_dist_init(ffb_dist** dist, int rank, int nranks, const void* host_id128);
+int ffb_dist_destroy(ffb_dist* dist);
+int ffb_dist_info(const ffb_dist* dist, int* rank, int* nranks);
+int ffb_dist_alltoall(ffb_dist* dist, const void* sendbuf, void* recvbuf, size_t block_bytes);
+int ffb_plan_create_dist(ffb_plan** plan, int ndim, const int64_t* n, int dtype, ffb_dist* dist, int nchunks /* 0 = default */);
 
 /* ---------------------------------------------------------------- grid-side kernels (src/domains.jl)
  * wavenumber vectors `k, l, m, kr` (:77-78,193-195,333-336): fftfreq/rfftfreq computed in Float64, stored as T. */
@@ -203,6 +217,7 @@ typedef struct {
   const void* kappa;     /* device real array (nx) for FFB_CALCN_DIFFUSION */
   int coef_dtype;        /* storage of ETD coefficients: FFB_F64 (reference-faithful) or dtype */
   int fused;             /* 1: fold spectral multiplies / products / dealias into FFT passes where implemented */
+  ffb_dist* dist;        /* non-NULL: slab-decomposed 3-D problem; all arrays are the local slabs (see ffb_plan_create_dist) */
 } ffb_problem_config;
 
 int ffb_problem_create(ffb_problem** prob, const ffb_problem_config* cfg);

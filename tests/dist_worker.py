@@ -1,0 +1,69 @@
+"""Worker run under torchrun (one process per GPU): slab-decomposed FFT and Burgers problem against the CPU oracle.
+Exit code 0 = parity green on every rank.  Usage: torchrun --nproc-per-node P tests/dist_worker.py [quick]"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    import fourierflows_jl_b200 as ff
+    from fourierflows_jl_b200 import _lib as L
+    import oracle as fo
+    from util import relerr
+
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    L.call("ffb_set_device", local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, P = dist.get_rank(), dist.get_world_size()
+    comm = ff.Dist.from_torch()
+    worst = 0.0
+    for shape, T, tol in (((64, 32, 64), np.float64, 1e-12), ((32, 64, 16 * P), np.float32, 1e-5), ((256, 256, 256), np.float64, 1e-12)):
+        rng = np.random.default_rng(5)
+        x = np.asfortranarray(rng.standard_normal(shape).astype(T))
+        ref = fo.RfftPlan(shape, T) * x.astype(np.float64)
+        for nch in (0, 1):
+            plan = ff.DistPlan(shape, T, comm, nchunks=nch)
+            xl = ff.DevArray.from_numpy(ff.physical_slab(x, P, rank))
+            xh = plan * xl
+            e1 = relerr(xh.to_numpy(), ff.spectral_slab(ref, P, rank))
+            back = plan.solve(xh)
+            e2 = relerr(back.to_numpy(), ff.physical_slab(x, P, rank))
+            e3 = 0.0 if np.array_equal(xl.to_numpy(), ff.physical_slab(x, P, rank)) else 1.0
+            worst = max(worst, e1 / tol, e2 / tol, e3)
+            if rank == 0:
+                print(f"dist fft {shape} {np.dtype(T).name} chunks={nch}: fwd {e1:.2e} rt {e2:.2e} [{plan.describe()}]", flush=True)
+    # slab-decomposed Burgers problem (configs C4 / C5 shape), C-driven, vs the single-process oracle
+    for stepper, T, tol in (("FilteredRK4", np.float64, 1e-12), ("ETDRK4", np.float32, 1e-5), ("LSRK54", np.float32, 1e-5)):
+        n = (64, 64, 64)
+        ob = fo.Burgers3D.Problem(nx=64, kappa=1e-3, dt=1e-3, stepper=stepper, T=T)
+        c0 = fo.random_phase_field(n, 2 * np.pi, 4.0, slope=0, seed=1234, T=T)
+        ob.grid.rfftplan.mul(ob.sol, c0)
+        cp = ff.CProblem(n, 2 * np.pi, stepper=stepper, dt=1e-3, calcN="burgers3d", nu=1e-3, T=T, dist=comm)
+        cp.set_physical(ff.physical_slab(c0, P, rank))
+        for s in range(3):
+            cp.stepforward(1)
+            fo.stepforward(ob, 1)
+            e = relerr(cp.sol.to_numpy(), ff.spectral_slab(ob.sol, P, rank))
+            worst = max(worst, e / ((s + 1) * tol))
+        if rank == 0:
+            print(f"dist burgers {stepper} {np.dtype(T).name}: rel-L2 after 3 steps {e:.2e}", flush=True)
+    t = torch.tensor([worst], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ok = float(t.item()) <= 1.0
+    if rank == 0:
+        print("DIST PARITY", "OK" if ok else f"FAILED (worst ratio {float(t.item()):.2f})", flush=True)
+    comm.close()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,104 @@
+"""Host-side logic of the slab decomposition with world_size = 2 over gloo (no GPU): rendezvous + NCCL unique-id
+broadcast plumbing, slab partitioning, and the exchange layout of csrc/fft_plan.cu::exec_dist restated in NumPy
+(y-pass output written destination-rank-major [peer][kx, y_local, z_local]; blocks received into (nkr, ny/P, nz))."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+import oracle  # noqa: F401  (tests may use the oracle)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    import scipy.fft as sfft
+    import torch.distributed as dist
+    import fourierflows_jl_b200 as ff
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # 1. the plumbing bench.py / Dist.from_torch use: rank 0 creates the 128-byte id, everyone receives the same bytes
+        obj = [ff.Dist.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0)
+        ids = [None] * world
+        dist.all_gather_object(ids, obj[0])
+        assert all(i == ids[0] for i in ids) and len(ids[0]) == 128
+        # 2. forward slab transform restated with the C code's layout, exchange over gloo
+        nx, ny, nz = 16, 8, 12
+        P = world
+        rng = np.random.default_rng(0)
+        x = np.asfortranarray(rng.standard_normal((nx, ny, nz)))
+        ref = sfft.rfftn(x, axes=(2, 1, 0))
+        nkr, nyl, nzl = nx // 2 + 1, ny // P, nz // P
+        xl = ff.physical_slab(x, P, rank)
+        a = sfft.fft(sfft.rfft(xl, axis=0), axis=1)                       # local x r2c + y c2c: (nkr, ny, nzl)
+        send = np.zeros((P, nkr, nyl, nzl), dtype=complex)                # [peer][kx, y_local, z_local]
+        for y in range(ny):
+            send[y // nyl, :, y % nyl, :] = a[:, y, :]                    # the segmented output stride of the y-pass
+        blocks = [None] * P
+        for src in range(P):
+            got = [None] * P if rank == src else None
+            # all-to-all via gather/scatter objects (gloo has no all_to_all)
+            gathered = [None] * P
+            dist.all_gather_object(gathered, send[src])
+            if rank == src:
+                blocks = gathered
+        recv = np.zeros((nkr, nyl, nz), dtype=complex, order="F")
+        for s in range(P):
+            recv[:, :, s * nzl:(s + 1) * nzl] = blocks[s]                 # block from rank s lands at z = s*nzl + z_local
+        out = sfft.fft(recv, axis=2)
+        err = np.linalg.norm(out - ff.spectral_slab(ref, P, rank)) / np.linalg.norm(ref)
+        assert err < 1e-13, err
+        # 3. alias ranges on the slab
+        lal = ff.getaliasedwavenumbers(ny, ny // 2 + 1, 1 / 3)[0]
+        loc = ff.local_alias_range(lal, ny, P, rank)
+        mask = np.zeros(ny, bool)
+        mask[lal[0] - 1:lal[1]] = True
+        lo, hi = ff.slab_range(ny, P, rank)
+        expect = mask[lo:hi]
+        mine = np.zeros(nyl, bool)
+        if loc:
+            mine[loc[0] - 1:loc[1]] = True
+        assert np.array_equal(mine, expect)
+        q.put((rank, "ok"))
+    except Exception as e:  # noqa: BLE001
+        q.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_slab_logic_world_size_2_gloo():
+    import torch.multiprocessing as mp
+    import __graft_entry__ as ge
+    ge.build()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] == "ok" for r in res), res
+
+
+def test_partition_helpers():
+    import fourierflows_jl_b200 as ff
+    assert ff.slab_range(1024, 8, 3) == (384, 512)
+    assert ff.local_alias_range((342, 683), 1024, 8, 2) == (86, 128)
+    assert ff.local_alias_range((342, 683), 1024, 8, 7) is None
+    assert ff.local_alias_range(None, 1024, 8, 0) is None
+    with pytest.raises(ff.FFBError):
+        ff.slab_range(10, 4, 0)
+    # 0.94 GB per GPU per 3-D FFT at 1024^3 Float64 on 8 GPUs
+    assert abs(ff.exchange_bytes_per_rank((1024, 1024, 1024), 8, 8) / 1e9 - 0.94) < 0.01
