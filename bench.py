@@ -1,12 +1,17 @@
 #!/usr/bin/env python
-"""Benchmark of the pseudospectral time-stepping hot path (BASELINE.json metric: ETDRK4 steps/s and Gpt*steps/s).
+"""Benchmark of the pseudospectral time-stepping hot path (BASELINE.json metric: ETDRK4 steps/s and Gpt*steps/s at
+8192^2 / 2048^3 on 1-8 B200; FFT % of HBM peak).
 
     python bench.py --gpus N --steps K --warmup W            # this library on N B200s (torchrun for N > 1)
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path restated (oracle), host cores
 
-One "step" = one ETDRK4 `stepforward!` (4 calcN! with 5 2-D FFTs each + 4 fused stage kernels) of the 2-D vorticity
-problem (user calcN! + dealias!) on the 8192^2 Float64 grid: config C3 of BASELINE.json / SURVEY 8d, the configuration
-the metric is quoted on for one GPU.  Prints ONE JSON line (rank 0).
+Workloads (one "step" = one ETDRK4 `stepforward!`: 4 calcN! + 4 fused stage kernels):
+  N = 1 : config C3 -- 2-D vorticity (user calcN! + dealias!) on TwoDGrid 8192^2 Float64, the configuration the metric
+          is quoted on for one GPU.
+  N > 1 : config C5 -- 3-D Burgers-like equation on ThreeDGrid (2048, 2048, 256*N) Float32, slab-decomposed with NCCL
+          all-to-all transposes; weak scaling in z, reaching the 2048^3 grid of the metric at N = 8.
+`value` is Gpt*steps/s (grid points x steps / s / 1e9) so that all N share one unit; `steps_per_s` is reported beside it.
+Prints ONE JSON line (rank 0).
 """
 import argparse
 import ctypes as C
@@ -22,12 +27,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-NU, DT, K0 = 1e-4, 1e-3, 64.0
-
-
-def work(n, d=2):
-    """N log2 N work model used to scale bounded CPU samples to the full grid."""
-    return float(n) ** d * np.log2(float(n) ** d)
+NVLINK_GBS = 770.0  # measured peer copy per direction per GPU (B200_PROFILING.md)
 
 
 def hbm_peak():
@@ -37,20 +37,106 @@ def hbm_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-# ------------------------------------------------------------------------------------------------ byte model
-def step_bytes(n, es=8):
-    """Algorithmic HBM bytes of one ETDRK4 step of the 2-D vorticity problem."""
-    nkr = n // 2 + 1
-    S, P, R = nkr * n * 2 * es, n * n * es, nkr * n * es
-    fft = P + 3 * S
-    calcN = (S + R + 2 * S) + 3 * fft + 5 * P + 2 * fft + 3 * S       # prep (no zeta_h copy) + 3 irfft + products + 2 rfft + combine
-    stages = (3 * S + 2 * R) * 2 + (4 * S + 2 * R) + (6 * S + 4 * R)   # substep12 x2, substep3, update (dense real Float64 coefficients)
-    return 4 * calcN + stages, fft
+def nlogn(shape):
+    n = float(np.prod([float(s) for s in shape]))
+    return n * np.log2(n)
+
+
+# ------------------------------------------------------------------------------------------------ workloads
+class Vorticity2D:
+    """C3 of SURVEY 8d: TwoDGrid(nx=n, Lx=2pi, aliased_fraction=1/3), L = -nu*Krsq, nu=1e-4, dt=1e-3, random-phase IC."""
+    nu, dt, K0 = 1e-4, 1e-3, 64.0
+    dtype, T = "f64", np.float64
+
+    def __init__(self, n, world):
+        self.shape, self.world = (n, n), 1
+        self.name = f"C3: 2-D vorticity ETDRK4 {n}^2 Float64 (TwoDGrid, aliased_fraction=1/3, nu={self.nu}, dt={self.dt}), random-phase IC seed 1234"
+        self.parallelism = "single GPU" if world == 1 else f"{world} independent replicas"
+        self.replicas = world
+
+    def points(self):
+        return float(np.prod(self.shape))
+
+    def bytes_per_step(self):
+        n, es = self.shape[0], 8
+        nkr = n // 2 + 1
+        S, P, R = nkr * n * 2 * es, n * n * es, nkr * n * es
+        fft = P + 3 * S
+        calcN = (S + R + 2 * S) + 3 * fft + 5 * P + 2 * fft + 3 * S      # prep (no zeta_h copy) + 3 irfft + products + 2 rfft + combine
+        stages = (3 * S + 2 * R) * 2 + (4 * S + 2 * R) + (6 * S + 4 * R)  # dense real Float64 coefficients
+        return 4 * calcN + stages, fft, 0.0
+
+    def make_gpu(self, ff, fo, rank, comm):
+        prob = ff.CProblem(self.shape, 2 * np.pi, stepper="ETDRK4", dt=self.dt, calcN="vorticity2d", nu=self.nu, T=self.T)
+        prob.set_physical(fo.random_phase_field(self.shape, 2 * np.pi, self.K0, slope=-1.0, seed=1234 + rank))
+        return prob
+
+    def fft_plan(self, ff, L, comm):
+        return ff.Plan(self.shape, self.T, L.FFB_R2C)
+
+    def make_cpu(self, fo, n_sample):
+        prob = fo.TwoDNavierStokes.Problem(nx=n_sample, nu=self.nu, dt=self.dt, stepper="ETDRK4")
+        z0 = fo.random_phase_field((n_sample, n_sample), 2 * np.pi, self.K0 * n_sample / self.shape[0], slope=-1.0, seed=1234)
+        prob.grid.rfftplan.mul(prob.sol, z0)
+        return prob, (n_sample, n_sample)
+
+
+class Burgers3D:
+    """C5 of SURVEY 8d: ThreeDGrid Float32, L = -kappa*Krsq, N = -1/2 im kr rfft(irfft(sol)^2) + dealias!, ETDRK4 with
+    T-width coefficients (the reference's Float64 coefficients do not fit: SURVEY 8d C5), slab-decomposed."""
+    kappa, dt, K0 = 1e-3, 1e-3, 32.0
+    dtype, T = "f32", np.float32
+
+    def __init__(self, nxy, nz_per_gpu, world):
+        self.shape, self.world = (nxy, nxy, nz_per_gpu * world), world
+        self.name = (f"C5: 3-D Burgers-like ETDRK4 {self.shape} Float32 (ThreeDGrid, aliased_fraction=1/3, kappa={self.kappa}, dt={self.dt}), "
+                     f"slab-decomposed over {world} GPUs, weak scaling in z ({nz_per_gpu} planes per GPU), random-phase IC")
+        self.parallelism = f"slab decomposition x{world}: physical z-slabs <-> spectral y-slabs, one NCCL all-to-all per 3-D transform"
+        self.replicas = 1
+
+    def points(self):
+        return float(np.prod(self.shape))
+
+    def bytes_per_step(self):
+        nx, ny, nz = self.shape
+        es = 4
+        nkr = nx // 2 + 1
+        S, P, R = nkr * ny * nz * 2 * es, nx * ny * nz * es, nkr * ny * nz * es
+        fft = P + 5 * S
+        calcN = 2 * fft + 2 * P + 2 * S
+        stages = (3 * S + 2 * R) * 2 + (4 * S + 2 * R) + (6 * S + 4 * R)
+        w = self.world
+        nvlink_per_gpu = 8 * (S / w) * (w - 1) / w   # 8 transforms per step, S/P*(P-1)/P bytes out per GPU each
+        return 4 * calcN + stages, fft, nvlink_per_gpu
+
+    def make_gpu(self, ff, fo, rank, comm):
+        prob = ff.CProblem(self.shape, 2 * np.pi, stepper="ETDRK4", dt=self.dt, calcN="burgers3d", nu=self.kappa, T=self.T,
+                           coef_dtype=np.float32, dist=comm)
+        # synthetic random field generated per slab on the device side of the API (rfft of uniform noise would need the
+        # full grid on one host): seeded white noise, smoothed by a few diffusion-dominated steps during warm-up
+        rng = np.random.default_rng(1234 + rank)
+        sl = rng.standard_normal(prob.physical_shape, dtype=np.float32)
+        prob.set_physical(np.asfortranarray(0.1 * sl))
+        return prob
+
+    def fft_plan(self, ff, L, comm):
+        return ff.DistPlan(self.shape, self.T, comm)
+
+    def make_cpu(self, fo, n_sample):
+        prob = fo.Burgers3D.Problem(nx=n_sample, kappa=self.kappa, dt=self.dt, stepper="ETDRK4", T=self.T)
+        c0 = 0.1 * np.random.default_rng(1234).standard_normal((n_sample,) * 3).astype(np.float32)
+        prob.grid.rfftplan.mul(prob.sol, np.asfortranarray(c0))
+        return prob, (n_sample,) * 3
+
+
+def make_workload(args, world):
+    if world == 1 or args.workload == "c3":
+        return Vorticity2D(args.n, world)
+    return Burgers3D(args.n3, args.nz_per_gpu, world)
 
 
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
@@ -71,47 +157,49 @@ class ClockSampler:
     def stop(self):
         if self.proc:
             self.proc.terminate()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        num = lambda s: s.replace(".", "").isdigit()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and num(r[1])]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and num(r[2])]
+        pw = [float(r[3]) for r in self.rows if len(r) >= 8 and num(r[3])]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for r in self.rows if len(r) >= 8 for i in range(4) if r[4 + i].lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm)}
 
 
-# ------------------------------------------------------------------------------------------------ reference arm / cpu baseline
-def cpu_arm(n_sample, steps, warmup, n_full):
+# ------------------------------------------------------------------------------------------------ CPU arms
+def cpu_arm(wl, n_sample, steps, warmup):
     """The reference's CPU path restated (oracle: NumPy + pocketfft with all host threads) on a bounded sample grid;
-    steps/s scaled to the full grid by the N log2 N work model."""
+    throughput scaled to the full grid by the N log2 N work model."""
     import oracle as fo
     cores = os.cpu_count() or 1
     fo.set_fft_workers(cores)
-    prob = fo.TwoDNavierStokes.Problem(nx=n_sample, nu=NU, dt=DT, stepper="ETDRK4")
-    z0 = fo.random_phase_field((n_sample, n_sample), 2 * np.pi, K0 * n_sample / n_full, slope=-1.0, seed=1234)
-    prob.grid.rfftplan.mul(prob.sol, z0)
+    prob, sshape = wl.make_cpu(fo, n_sample)
     fo.stepforward(prob, warmup)
     t0 = time.perf_counter()
     fo.stepforward(prob, steps)
     dt = (time.perf_counter() - t0) / steps
-    scale = work(n_sample) / work(n_full)
     assert np.isfinite(prob.sol).all()
-    return {"value": scale / dt, "unit": "steps/s", "cores": cores, "kind": "port",
-            "sample": f"{steps} ETDRK4 step(s) of the same 2-D vorticity problem at {n_sample}^2 Float64 ({dt:.3f} s/step measured, pocketfft workers={cores}), "
-                      f"scaled to {n_full}^2 by N*log2(N) (x{scale:.4f}); reference CPU path restated in NumPy, not FFTW (no Julia/FFTW in the image)"}
+    scale = nlogn(sshape) / nlogn(wl.shape)
+    sps = scale / dt
+    return {"value": sps * wl.points() / 1e9, "unit": "Gpt*steps/s", "steps_per_s": sps, "cores": cores, "kind": "port",
+            "sample": f"{steps} ETDRK4 step(s) of the same problem on a {'x'.join(map(str, sshape))} {wl.dtype} grid ({dt:.3f} s/step measured, "
+                      f"pocketfft workers={cores}), scaled to {'x'.join(map(str, wl.shape))} by N*log2(N) (x{scale:.3e}); reference CPU path "
+                      f"restated in NumPy + pocketfft, not FFTW (no Julia/FFTW in the image)"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_full = args.n
-    n_sample = min(n_full, 2048)
-    cb = cpu_arm(n_sample, args.steps, max(1, args.warmup), n_full)
-    v = cb["value"]
-    line = {"impl": "reference", "metric": "ETDRK4 steps/s (2-D vorticity, user calcN! + dealias!)", "value": v, "unit": "steps/s",
-            "gpt_steps_per_s": v * n_full * n_full / 1e9, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"C3: 2-D vorticity ETDRK4 {n_full}^2 Float64 (TwoDGrid, aliased_fraction=1/3, nu={NU}, dt={DT})"},
-            "cpu_baseline": cb, "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    wl = make_workload(args, args.gpus)
+    n_sample = min(wl.shape[0], 2048) if len(wl.shape) == 2 else min(wl.shape[0], 128)
+    cb = cpu_arm(wl, n_sample, args.steps, max(1, args.warmup))
+    line = {"impl": "reference", "metric": "ETDRK4 Gpt*steps/s (grid points x steps per second / 1e9)", "value": cb["value"], "unit": "Gpt*steps/s",
+            "steps_per_s": cb["steps_per_s"], "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 / cb["steps_per_s"], "higher_is_better": True, "scaling": "weak" if args.gpus > 1 else "strong",
+            "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic", "config": {"workload": wl.name, "grid": list(wl.shape)},
+            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "Gpt*steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
@@ -129,12 +217,15 @@ def run_gpu(args):
         raise SystemExit("bench.py needs a CUDA device: libfourierflows_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     L.call("ffb_set_device", local)
+    comm = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    wl = make_workload(args, world)
+    if world > 1 and wl.replicas == 1:
+        comm = ff.Dist.from_torch()
     stream = torch.cuda.Stream()
     L.call("ffb_set_stream", stream.cuda_stream)
-    n = args.n
     peak, peak_src = hbm_peak()
 
     def barrier():
@@ -143,10 +234,16 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        import torch.distributed as dist
+        t = torch.tensor([v], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     with torch.cuda.stream(stream):
-        prob = ff.CProblem((n, n), 2 * np.pi, stepper="ETDRK4", dt=DT, calcN="vorticity2d", nu=NU, T=np.float64)
-        z0 = fo.random_phase_field((n, n), 2 * np.pi, K0, slope=-1.0, seed=1234 + rank)
-        prob.set_physical(z0)
+        prob = wl.make_gpu(ff, fo, rank, comm)
         # ---------------- value: K steps, state resident in HBM ----------------
         prob.stepforward(args.warmup)
         barrier()
@@ -158,44 +255,41 @@ def run_gpu(args):
         prob.stepforward(args.steps)
         e1.record(stream)
         barrier()
-        ms = e0.elapsed_time(e1)
+        ms_per_step = max_over_ranks(e0.elapsed_time(e1)) / args.steps
         launches = ff.launch_count() - l0
         clocks = sampler.stop()
-        if world > 1:
-            import torch.distributed as dist
-            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        ms_per_step = ms / args.steps
-        assert np.isfinite(prob.sol.to_numpy()[:8, :8]).all()
-        # ---------------- per-kernel roofline: same steps with CUDA events around every kernel launch ----------------
+        head = prob.sol.view(shape=(64,), dtype=prob.sol.dtype).to_numpy()
+        assert np.isfinite(head).all(), "state diverged"
+        # ---------------- per-kernel roofline: the same steps with CUDA events around every kernel launch ----------------
         ff.prof_enable(True)
-        prob.stepforward(min(args.steps, 5))
+        prob.stepforward(min(args.steps, 4))
         rep = ff.prof_report()
         ff.prof_enable(False)
         tot_ms = sum(r["ms"] for r in rep)
         rep.sort(key=lambda r: -r["ms"])
-        top = rep[0]
+        hbm_rep = [r for r in rep if r["bytes"] > 0]
+        top = hbm_rep[0]
         kernels = [{"name": r["name"], "share": round(r["ms"] / tot_ms, 4), "us_per_launch": round(1e3 * r["ms"] / r["launches"], 2),
                     "gbs": round(r["bytes"] / r["ms"] / 1e6, 1), "frac": round(r["bytes"] / r["ms"] / 1e6 / peak, 4)} for r in rep]
         roofline = {"bound": "hbm", "kernel": top["name"], "achieved": top["bytes"] / top["ms"] / 1e6, "peak": peak, "unit": "GB/s",
                     "frac": top["bytes"] / top["ms"] / 1e6 / peak, "traffic": None, "peak_source": peak_src,
                     "share_of_step": top["ms"] / tot_ms, "algorithmic_bytes_per_launch": top["bytes"] / top["launches"]}
-        # ---------------- FFT % of HBM peak: standalone 2-D r2c / c2r at the same size ----------------
-        plan = ff.Plan((n, n), np.float64, L.FFB_R2C)
-        x = ff.DevArray.zeros(np.float64, (n, n))
-        xh = ff.DevArray.zeros(np.complex128, plan.spectral_shape)
+        # ---------------- FFT % of HBM peak: standalone r2c / c2r at the same size ----------------
+        plan = wl.fft_plan(ff, L, comm)
+        x = ff.DevArray.zeros(wl.T, plan.physical_shape)
+        xh = ff.DevArray.zeros(ff.cxtype(wl.T), plan.spectral_shape)
         fft_ms = {}
         for name, fn in (("rfft", lambda: plan.mul(xh, x)), ("irfft", lambda: plan.ldiv(x, xh))):
             for _ in range(3):
                 fn()
+            barrier()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(stream)
             for _ in range(10):
                 fn()
             b.record(stream)
-            b.synchronize()
-            fft_ms[name] = a.elapsed_time(b) / 10
+            barrier()
+            fft_ms[name] = max_over_ranks(a.elapsed_time(b)) / 10
         del x, xh, plan
         # ---------------- e2e: host buffers in, host buffers out, through the C ABI ----------------
         S = prob.sol.nbytes
@@ -207,37 +301,46 @@ def run_gpu(args):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(stream)
         for _ in range(ke):
-            L.call("ffb_h2d", prob.sol.ptr, hp, S)      # this step's input state from pinned host memory
+            L.call("ffb_h2d", prob.sol.ptr, hp, S)      # this step's input state (this rank's slab) from pinned host memory
             prob.stepforward(1)                          # public call: ffb_step
             L.call("ffb_d2h", hp, prob.sol.ptr, S)       # result back to the host (blocking)
         b.record(stream)
         barrier()
-        e2e_ms = a.elapsed_time(b) / ke
+        e2e_ms = max_over_ranks(a.elapsed_time(b)) / ke
         L.call("ffb_host_free_pinned", hp)
         dev_bytes = prob.device_bytes()
 
-    total_bytes, fft_bytes = step_bytes(n)
-    value = world * 1e3 / ms_per_step  # independent replicas when world > 1 (see config.parallelism)
+    total_bytes, fft_bytes, nvlink_bytes = wl.bytes_per_step()
+    sps = wl.replicas * 1e3 / ms_per_step
+    gpt = sps * wl.points() / 1e9
+    hbm_ms = total_bytes / (world if wl.replicas == 1 else 1) / peak / 1e6
+    nvl_ms = nvlink_bytes / NVLINK_GBS / 1e6
+    fftw = (world if wl.replicas == 1 else 1)
     line = {
-        "metric": "ETDRK4 steps/s (2-D vorticity, user calcN! + dealias!)", "value": value, "unit": "steps/s",
-        "gpt_steps_per_s": value * n * n / 1e9,
+        "metric": "ETDRK4 Gpt*steps/s (grid points x steps per second / 1e9)", "value": gpt, "unit": "Gpt*steps/s", "steps_per_s": sps,
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "weak" if world > 1 else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"C3: 2-D vorticity ETDRK4 {n}^2 Float64 (TwoDGrid, aliased_fraction=1/3, nu={NU}, dt={DT}), random-phase IC seed 1234",
-                   "grid": [n, n], "stepper": "ETDRK4", "parallelism": "single GPU" if world == 1 else f"{world} independent replicas",
-                   "l2": f"every array is {S / 1e6:.0f} MB > 126 MB L2; no flush needed", "device_bytes": dev_bytes},
-        "step_roofline": {"algorithmic_bytes_per_step": total_bytes, "ms_at_peak": total_bytes / peak / 1e6,
-                          "frac": (total_bytes / peak / 1e6) / ms_per_step, "peak_gbs": peak, "peak_source": peak_src},
+        "scaling": "weak" if world > 1 else "strong", "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic",
+        "config": {"workload": wl.name, "grid": list(wl.shape), "stepper": "ETDRK4", "parallelism": wl.parallelism,
+                   "l2": "every array is far larger than the 126 MB L2; no flush needed", "device_bytes_per_gpu": dev_bytes},
+        "step_roofline": {"algorithmic_hbm_bytes_per_step": total_bytes, "nvlink_bytes_per_gpu_per_step": nvlink_bytes,
+                          "hbm_ms_at_peak": hbm_ms, "nvlink_ms_at_770": nvl_ms, "ms_at_roofline_overlapped": max(hbm_ms, nvl_ms),
+                          "frac": max(hbm_ms, nvl_ms) / ms_per_step, "frac_non_overlapped": (hbm_ms + nvl_ms) / ms_per_step,
+                          "peak_gbs": peak, "peak_source": peak_src},
         "fft": {"rfft_ms": fft_ms["rfft"], "irfft_ms": fft_ms["irfft"], "algorithmic_bytes": fft_bytes,
-                "rfft_frac_hbm_peak": fft_bytes / fft_ms["rfft"] / 1e6 / peak, "irfft_frac_hbm_peak": fft_bytes / fft_ms["irfft"] / 1e6 / peak},
+                "rfft_frac_hbm_peak": fft_bytes / fftw / fft_ms["rfft"] / 1e6 / peak, "irfft_frac_hbm_peak": fft_bytes / fftw / fft_ms["irfft"] / 1e6 / peak,
+                "alltoall_gbs_per_gpu_rfft": (nvlink_bytes / 8) / fft_ms["rfft"] / 1e6 if nvlink_bytes else None},
         "roofline": roofline, "kernels": kernels,
-        "e2e": {"value": world * 1e3 / e2e_ms, "unit": "steps/s", "h2d_bytes_per_step": S, "d2h_bytes_per_step": S, "ms_per_step": e2e_ms},
+        "e2e": {"value": wl.replicas * 1e3 / e2e_ms * wl.points() / 1e9, "unit": "Gpt*steps/s", "steps_per_s": wl.replicas * 1e3 / e2e_ms,
+                "h2d_bytes_per_step": S * world, "d2h_bytes_per_step": S * world, "ms_per_step": e2e_ms},
         "gpu_launches": launches, "clocks": clocks,
     }
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_arm(min(n, 4096) if args.cpu_sample == 0 else args.cpu_sample, 1, 0, n)
+            line["cpu_baseline"] = cpu_arm(wl, args.cpu_sample or min(wl.shape[0], 4096), 1, 0)
         print(json.dumps(line))
+    del prob
+    if comm is not None:
+        comm.close()
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
@@ -249,8 +352,11 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=8192, help="grid size per side (default: the C3 configuration)")
-    ap.add_argument("--cpu-sample", type=int, default=0, help="grid size of the cpu_baseline sample (default 4096)")
+    ap.add_argument("--workload", default="auto", choices=["auto", "c3", "c5"])
+    ap.add_argument("--n", type=int, default=8192, help="C3 grid size per side")
+    ap.add_argument("--n3", type=int, default=2048, help="C5 grid size in x and y")
+    ap.add_argument("--nz-per-gpu", type=int, default=256, help="C5 z-planes per GPU (weak scaling; 256 x 8 = 2048)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="grid size of the cpu_baseline sample (default 4096 for C3)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -2,6 +2,7 @@
 // `mul!` / `ldiv!` executions on `grid.rfftplan` / `grid.fftplan` (src/diffusion.jl:137,139,154,155,171).
 // A d-dimensional transform is one 1-D pass per dimension (P + (2d-1) S bytes of HBM traffic for r2c / c2r).
 #include <cmath>
+#include <cstdlib>
 #include <map>
 #include <string>
 #include <vector>
@@ -56,6 +57,12 @@ struct DimTables {
   cx<T>* tw = nullptr;   // pow2 per-pass twiddles
   cx<T>* wN = nullptr;   // generic: exp(-2 pi i q / N), q < N
   cx<T>* twr = nullptr;  // split step: exp(-i pi k / N), k <= N (dim 0 of R2C plans only)
+  // four-step split of a long strided line: N = N1*N2, two short sub-passes with wide rows
+  bool four = false;
+  int N1 = 0, N2 = 0;
+  cx<T>* tw1 = nullptr;  // base twiddles of the length-N1 sub-transform
+  cx<T>* tw2 = nullptr;  // base twiddles of the length-N2 sub-transform
+  cx<T>* twN = nullptr;  // exp(-2 pi i q / N), q < N: inter-pass twiddles
 };
 
 }  // namespace ffb
@@ -77,6 +84,31 @@ struct ffb_plan {
 
 namespace ffb {
 
+// base twiddles of the register-resident plan for length N: for each pass with Ns > 1, exp(-2 pi i a/(Ns r)), a < Ns
+template <typename T>
+static int build_pow2_tw(int N, cx<T>** dev) {
+  int rad[8];
+  const int np = pow2_radices(N, rad);
+  std::vector<cx<T>> h;
+  int Ns = 1;
+  for (int i = 0; i < np; ++i) {
+    const int r = rad[i];
+    if (Ns > 1)
+      for (int a = 0; a < Ns; ++a) h.push_back(unit_root<T>((long long)a, (long long)Ns * r));
+    Ns *= r;
+  }
+  if (h.empty()) h.push_back(mk<T>(1, 0));
+  return upload(h, dev);
+}
+
+// Strided lines at least this long are transformed as a four-step pair of short sub-passes (measured: one register-resident
+// pass over 8192 F64 points reaches 1.6 TB/s because a CTA can own only one 16-byte wide column; sub-passes of 64 / 128
+// points own 32-64 columns and run near the HBM roofline).  FFB_FOURSTEP_MIN overrides (0 disables).
+template <typename T> static int fourstep_min() {
+  if (const char* e = getenv("FFB_FOURSTEP_MIN")) { const int v = atoi(e); return v > 0 ? v : (1 << 30); }
+  return sizeof(T) == 8 ? 4096 : 8192;
+}
+
 template <typename T>
 static int build_tables(ffb_plan* pl) {
   for (int d = 0; d < pl->ndim; ++d) {
@@ -87,18 +119,23 @@ static int build_tables(ffb_plan* pl) {
     tb->N = N;
     int rad[8];
     const int np = pow2_radices(N, rad);
-    tb->pow2 = !(pl->flags & FFB_PLAN_FORCE_GENERIC) && is_pow2((uint64_t)N) && N >= 2 && N <= pow2_max_n(sizeof(T)) && np > 0;
-    if (tb->pow2) {
-      std::vector<cx<T>> h;
-      int Ns = 1;
-      for (int i = 0; i < np; ++i) {
-        const int r = rad[i];
-        if (Ns > 1)
-          for (int a = 0; a < Ns; ++a) h.push_back(unit_root<T>((long long)a, (long long)Ns * r));
-        Ns *= r;
-      }
-      if (h.empty()) h.push_back(mk<T>(1, 0));
-      int rc = upload(h, &tb->tw);
+    const bool allow = !(pl->flags & FFB_PLAN_FORCE_GENERIC) && is_pow2((uint64_t)N) && N >= 2;
+    tb->pow2 = allow && N <= pow2_max_n(sizeof(T)) && np > 0;
+    if (allow && d > 0 && N >= fourstep_min<T>() && N <= 65536) {
+      const int l2 = ilog2((uint64_t)N);
+      tb->four = true;
+      tb->N1 = 1 << (l2 / 2);
+      tb->N2 = N / tb->N1;
+      tb->pow2 = true;
+      int rc = build_pow2_tw<T>(tb->N1, &tb->tw1);
+      if (rc) return rc;
+      if ((rc = build_pow2_tw<T>(tb->N2, &tb->tw2))) return rc;
+      std::vector<cx<T>> h((size_t)N);
+      for (int q = 0; q < N; ++q) h[q] = unit_root<T>(q, N);
+      if ((rc = upload(h, &tb->twN))) return rc;
+      if (N <= pow2_max_n(sizeof(T)) && np > 0 && (rc = build_pow2_tw<T>(N, &tb->tw))) return rc;
+    } else if (tb->pow2) {
+      int rc = build_pow2_tw<T>(N, &tb->tw);
       if (rc) return rc;
     } else {
       std::vector<cx<T>> h((size_t)std::max(N, 1));
@@ -114,7 +151,8 @@ static int build_tables(ffb_plan* pl) {
       if (rc) return rc;
     }
     char buf[96];
-    snprintf(buf, sizeof(buf), "dim%d:N=%d:%s ", d, N, tb->pow2 ? "pow2-register-stockham" : "generic-mixed-radix");
+    if (tb->four) snprintf(buf, sizeof(buf), "dim%d:N=%d:pow2-four-step(%dx%d) ", d, N, tb->N1, tb->N2);
+    else snprintf(buf, sizeof(buf), "dim%d:N=%d:%s ", d, N, tb->pow2 ? "pow2-register-stockham" : "generic-mixed-radix");
     pl->desc += buf;
   }
   return FFB_OK;
@@ -125,7 +163,7 @@ static void free_tables(ffb_plan* pl) {
   for (int d = 0; d < pl->ndim; ++d) {
     auto* tb = reinterpret_cast<DimTables<T>*>(pl->tables[d]);
     if (!tb) continue;
-    cudaFree(tb->tw); cudaFree(tb->wN); cudaFree(tb->twr);
+    cudaFree(tb->tw); cudaFree(tb->wN); cudaFree(tb->twr); cudaFree(tb->tw1); cudaFree(tb->tw2); cudaFree(tb->twN);
     delete tb;
   }
 }
@@ -156,21 +194,29 @@ static int call_pow2(int N, int mode, int dir, const Pow2Params<T>& p, int gx, i
   return set_error(FFB_EUNSUPPORTED, "no register-resident FFT kernel for N=%d", N);
 }
 
-// Lines-per-CTA choice.  ROWS: enough lines for >= 256 threads.  COLS: as many adjacent columns as the thread and
-// shared-memory budgets allow, so each HBM access is W*sizeof(complex) wide (>= 128 B wherever it fits).
+// Lines-per-CTA choice (measured: tools/sweep_w.py, tools/sweep2.py, profiles/r01_sweep_*.log).  Throughput is set by how
+// many independent CTAs an SM can overlap, so CTAs are kept small.  ROWS: one line per CTA (>= 32 threads).
+// COLS: about 256 threads with W adjacent columns clamped to [64 B, 256 B] wide rows (Float64 4..16, Float32 8..32
+// columns; the twiddled four-step sub-pass likes 32).
 template <typename T>
 static int choose_w(int N, int mode, long long nlines) {
   const int R = pow2_points_per_thread(N);
   const int Tn = N / R;
   const int maxT = pow2_max_threads(sizeof(T));
   const size_t smem_cap = (size_t)max_smem_optin() - 1024;
+  const bool cols = (mode == C2C_COLS || mode == C2C_COLS_TW);
   int W = 1;
-  if (mode == C2C_COLS) {
-    const int want = (int)(256 / sizeof(cx<T>));  // 256-byte wide tiles
-    while (W * 2 <= want && Tn * W * 2 <= maxT && pow2_smem_bytes<T>(N, W * 2, mode) <= smem_cap) W *= 2;
-    while (Tn * W < 128 && Tn * W * 2 <= maxT && pow2_smem_bytes<T>(N, W * 2, mode) <= smem_cap) W *= 2;
+  if (cols) {
+    const int lo = sizeof(T) == 8 ? 4 : 8, hi = (sizeof(T) == 8 && mode == C2C_COLS) ? 16 : 32;
+    int want = std::max(lo, std::min(hi, 256 / std::max(Tn, 1)));
+    while (W < want && Tn * W * 2 <= maxT && pow2_smem_bytes<T>(N, W * 2, mode) <= smem_cap) W *= 2;
   } else {
-    while (Tn * W < 256 && Tn * W * 2 <= maxT && pow2_smem_bytes<T>(N, W * 2, mode) <= smem_cap) W *= 2;
+    while (Tn * W < 32 && Tn * W * 2 <= maxT && pow2_smem_bytes<T>(N, W * 2, mode) <= smem_cap) W *= 2;
+  }
+  // tuning overrides (measurement only): FFB_W_COLS / FFB_W_ROWS force the lines-per-CTA when legal
+  if (const char* e = getenv((mode == C2C_COLS || mode == C2C_COLS_TW) ? "FFB_W_COLS" : "FFB_W_ROWS")) {
+    const int w = atoi(e);
+    if (w >= 1 && Tn * w <= maxT && pow2_smem_bytes<T>(N, w, mode) <= smem_cap && ((mode != C2C_COLS && mode != C2C_COLS_TW) || is_pow2((uint64_t)w))) W = w;
   }
   while (W > 1 && W / 2 >= nlines) W /= 2;
   return W;
@@ -178,11 +224,14 @@ static int choose_w(int N, int mode, long long nlines) {
 
 // One register-resident pass over `nouter` outer blocks (gridDim.y chunks of <= 65535).
 struct SegStride { int seg = 0; long long stride = 0; };  // seg = 0: unsegmented
+// two-level outer index (four-step sub-passes): blockIdx.y = o_lo + mod*o_hi -> o_lo*os + o_hi*os2
+struct Outer2 { int mod = 0; long long nhi = 1, in_os2 = 0, out_os2 = 0; };
 
 template <typename T>
 static int pow2_pass(int N, int mode, int dir, const void* in, void* out, long long in_es, long long in_ls, long long in_os,
                      long long out_es, long long out_ls, long long out_os, long long nlines, long long nouter, T scale,
-                     const DimTables<T>* tb, cudaStream_t st, SegStride in_seg = SegStride(), SegStride out_seg = SegStride()) {
+                     const cx<T>* tw, const cx<T>* twr, cudaStream_t st, SegStride in_seg = SegStride(), SegStride out_seg = SegStride(),
+                     Outer2 o2 = Outer2(), const cx<T>* twN = nullptr, int twN_mask = 0) {
   Pow2Params<T> p;
   p.in_seg_mask = in_seg.seg ? in_seg.seg - 1 : 0x7fffffff; p.in_seg_shift = in_seg.seg ? ilog2((uint64_t)in_seg.seg) : 31;
   p.in_seg_stride = in_seg.stride;
@@ -190,23 +239,40 @@ static int pow2_pass(int N, int mode, int dir, const void* in, void* out, long l
   p.out_seg_stride = out_seg.stride;
   p.in_es = in_es; p.in_ls = in_ls; p.in_os = in_os;
   p.out_es = out_es; p.out_ls = out_ls; p.out_os = out_os;
+  p.in_os2 = o2.in_os2; p.out_os2 = o2.out_os2;
+  p.twN = twN; p.twN_mask = twN_mask;
   p.nlines = nlines;
   p.W = choose_w<T>(N, mode, nlines);
   p.scale = scale;
-  p.tw = tb->tw;
-  p.twr = tb->twr;
+  p.tw = tw;
+  p.twr = twr;
   const int R = pow2_points_per_thread(N);
   const int threads = (N / R) * p.W;
   const size_t smem = pow2_smem_bytes<T>(N, p.W, mode);
   const long long gx = (nlines + p.W - 1) / p.W;
   FFB_REQUIRE(gx < (1ll << 31), FFB_EUNSUPPORTED, "too many lines for one launch");
-  static const char* mode_names[4] = {"c2c_rows", "c2c_cols", "r2c_rows", "c2r_rows"};
+  static const char* mode_names[5] = {"c2c_rows", "c2c_cols", "r2c_rows", "c2r_rows", "c2c_cols_tw"};
   char pname[64];
   snprintf(pname, sizeof(pname), "fft_%s_%s_N%d", mode_names[mode], sizeof(T) == 8 ? "f64" : "f32", N);
   // algorithmic bytes: every element of the line set is read once and written once
-  const double lines = (double)nlines * (double)nouter;
+  const double lines = (double)nlines * (double)nouter * (double)(o2.mod ? o2.nhi : 1);
   const double in_elems = (mode == C2R_ROWS) ? N + 1 : N, out_elems = (mode == R2C_ROWS) ? N + 1 : N;
   ProfScope ps(pname, lines * (in_elems + out_elems) * sizeof(cx<T>));
+  if (o2.mod) {
+    // nouter = o2.mod low indices per high index; chunk over the high index so that gridDim.y <= 65535
+    FFB_REQUIRE(o2.mod <= 65535, FFB_EUNSUPPORTED, "four-step factor too large");
+    p.outer_mod = o2.mod;
+    const long long hchunk = std::max<long long>(1, 65535 / o2.mod);
+    for (long long h0 = 0; h0 < o2.nhi; h0 += hchunk) {
+      const long long cnt = std::min<long long>(hchunk, o2.nhi - h0);
+      p.in = reinterpret_cast<const cx<T>*>(in) + h0 * o2.in_os2;
+      p.out = reinterpret_cast<cx<T>*>(out) + h0 * o2.out_os2;
+      int rc = call_pow2<T>(N, mode, dir, p, (int)gx, (int)(cnt * o2.mod), threads, smem, st);
+      if (rc) return rc;
+    }
+    return FFB_OK;
+  }
+  p.outer_mod = 1 << 30;
   for (long long o0 = 0; o0 < nouter; o0 += 65535) {
     const long long cnt = std::min<long long>(65535, nouter - o0);
     p.in = reinterpret_cast<const cx<T>*>(in) + o0 * in_os;
@@ -215,6 +281,28 @@ static int pow2_pass(int N, int mode, int dir, const void* in, void* out, long l
     if (rc) return rc;
   }
   return FFB_OK;
+}
+
+// strided (column) pass along dimension d: one register-resident pass, or the four-step pair A (in place allowed) + B
+// (strictly out of place).  part: 0 = single pass, 1 = four-step A, 2 = four-step B.
+template <typename T>
+static int cols_pass(const DimTables<T>* tb, int part, long long inner, long long outer, const cx<T>* src, cx<T>* dst, int dir, T scale,
+                     cudaStream_t st) {
+  const int N = tb->N;
+  if (part == 0)
+    return pow2_pass<T>(N, C2C_COLS, dir, src, dst, inner, 1, inner * N, inner, 1, inner * N, inner, outer, scale, tb->tw, nullptr, st);
+  const int N1 = tb->N1, N2 = tb->N2;
+  Outer2 o2;
+  o2.nhi = outer; o2.in_os2 = inner * N; o2.out_os2 = inner * N;
+  if (part == 1) {  // length-N1 transforms over n1 (element stride N2*inner) for each n2, times exp(-/+2 pi i n2 k1/N)
+    o2.mod = N2;
+    return pow2_pass<T>(N1, C2C_COLS_TW, dir, src, dst, (long long)N2 * inner, 1, inner, (long long)N2 * inner, 1, inner, inner, N2, T(1), tb->tw1,
+                        nullptr, st, SegStride(), SegStride(), o2, tb->twN, N - 1);
+  }
+  // length-N2 transforms over n2 (stride inner) for each k1 (outer stride N2*inner); output index k1 + N1*k2
+  o2.mod = N1;
+  return pow2_pass<T>(N2, C2C_COLS, dir, src, dst, inner, 1, (long long)N2 * inner, (long long)N1 * inner, 1, inner, inner, N1, scale, tb->tw2, nullptr,
+                      st, SegStride(), SegStride(), o2);
 }
 
 // c2c pass along dimension d of a dense complex array with extents e[0..2] x nb (x fastest).
@@ -226,19 +314,89 @@ static int c2c_dim(ffb_plan* pl, int d, const long long e[3], long long nb, cons
   long long inner = 1, outer = nb;
   for (int i = 0; i < d; ++i) inner *= e[i];
   for (int i = d + 1; i < 3; ++i) outer *= e[i];
-  if (tb->pow2) {
+  if (tb->pow2 && tb->tw) {
     if (d == 0)
-      return pow2_pass<T>(N, C2C_ROWS, dir, src, dst, 1, N, 0, 1, N, 0, outer, 1, scale, tb, st);
-    return pow2_pass<T>(N, C2C_COLS, dir, src, dst, inner, 1, inner * N, inner, 1, inner * N, inner, outer, scale, tb, st);
+      return pow2_pass<T>(N, C2C_ROWS, dir, src, dst, 1, N, 0, 1, N, 0, outer, 1, scale, tb->tw, nullptr, st);
+    return cols_pass<T>(tb, 0, inner, outer, src, dst, dir, scale, st);
   }
+  FFB_REQUIRE(tb->wN, FFB_EUNSUPPORTED, "dimension %d of this plan mixes the arbitrary-size path with a four-step-only length", d);
   int rc = ensure_ws(pl, 2);
   if (rc) return rc;
   return generic_fft_axis<T>(src, dst, reinterpret_cast<cx<T>*>(pl->ws[0]), reinterpret_cast<cx<T>*>(pl->ws[1]), inner, N, outer,
                              dir, scale, tb->wN, st);
 }
 
+// All-power-of-two plans: a list of passes (x rows pass, then one single pass or a four-step pair per strided dimension)
+// is scheduled over {IN (never written), OUT, WS0, WS1} so that the result lands in OUT and strictly out-of-place passes
+// (r2c, c2r, four-step B) never alias.
+template <typename T>
+static int exec_pow2(ffb_plan* pl, const void* in, void* out, int dir) {
+  cudaStream_t st = current_stream();
+  FFB_REQUIRE(st, FFB_ECUDA, "no CUDA stream (no device?)");
+  const int nd = pl->ndim;
+  const long long nb = pl->nbatch;
+  struct Op { int kind, d, part; bool strict; };  // kind: 0 = c2c rows, 1 = r2c rows, 2 = c2r rows, 3 = strided pass
+  std::vector<Op> ops;
+  auto push_cols = [&](int d) {
+    auto* tb = reinterpret_cast<DimTables<T>*>(pl->tables[d]);
+    if (tb->four) { ops.push_back({3, d, 1, false}); ops.push_back({3, d, 2, true}); }
+    else ops.push_back({3, d, 0, false});
+  };
+  if (pl->kind == FFB_C2C) { ops.push_back({0, 0, 0, false}); for (int d = 1; d < nd; ++d) push_cols(d); }
+  else if (dir < 0) { ops.push_back({1, 0, 0, true}); for (int d = 1; d < nd; ++d) push_cols(d); }
+  else { for (int d = nd - 1; d >= 1; --d) push_cols(d); ops.push_back({2, 0, 0, true}); }
+  const int n = (int)ops.size();
+  enum { IN = 0, OUT = 1, WS0 = 2, WS1 = 3 };
+  std::vector<int> src(n), dst(n);
+  dst[n - 1] = OUT;
+  int need_ws = 0;
+  for (int i = n - 1; i >= 0; --i) {
+    if (i == 0) src[i] = IN;
+    else if (ops[i].strict) src[i] = (dst[i] != WS0) ? WS0 : WS1;
+    else src[i] = dst[i];
+    if (i > 0) dst[i - 1] = src[i];
+    need_ws = std::max(need_ws, std::max(src[i], dst[i]) - 1);
+  }
+  if (need_ws > 0) { int rc = ensure_ws(pl, need_ws); if (rc) return rc; }
+  auto buf = [&](int b) -> void* { return b == IN ? const_cast<void*>(in) : b == OUT ? out : pl->ws[b - WS0]; };
+  long double tot = 1;
+  for (int d = 0; d < nd; ++d) tot *= (long double)pl->n[d];
+  const T inv = (T)(1.0L / tot);
+  const long long e[3] = {pl->nc[0], pl->nc[1], pl->nc[2]};
+  auto* tb0 = reinterpret_cast<DimTables<T>*>(pl->tables[0]);
+  long long rows = nb;
+  for (int d = 1; d < nd; ++d) rows *= pl->n[d];
+  for (int i = 0; i < n; ++i) {
+    const Op& op = ops[i];
+    const void* s_ = buf(src[i]);
+    void* d_ = buf(dst[i]);
+    const T sc = (dir > 0 && i == n - 1) ? inv : T(1);
+    int rc;
+    if (op.kind == 0) rc = pow2_pass<T>(tb0->N, C2C_ROWS, dir, s_, d_, 1, tb0->N, 0, 1, tb0->N, 0, rows, 1, sc, tb0->tw, nullptr, st);
+    else if (op.kind == 1) rc = pow2_pass<T>(tb0->N, R2C_ROWS, -1, s_, d_, 1, tb0->N, 0, 1, e[0], 0, rows, 1, T(1), tb0->tw, tb0->twr, st);
+    else if (op.kind == 2) rc = pow2_pass<T>(tb0->N, C2R_ROWS, +1, s_, d_, 1, e[0], 0, 1, tb0->N, 0, rows, 1, sc, tb0->tw, tb0->twr, st);
+    else {
+      long long inner = 1, outer = nb;
+      for (int q = 0; q < op.d; ++q) inner *= e[q];
+      for (int q = op.d + 1; q < 3; ++q) outer *= e[q];
+      rc = cols_pass<T>(reinterpret_cast<DimTables<T>*>(pl->tables[op.d]), op.part, inner, outer, reinterpret_cast<const cx<T>*>(s_),
+                        reinterpret_cast<cx<T>*>(d_), dir, sc, st);
+    }
+    if (rc) return rc;
+  }
+  return FFB_OK;
+}
+
 template <typename T>
 static int exec(ffb_plan* pl, const void* in, void* out, int dir) {
+  {
+    bool allp = true;
+    for (int d = 0; d < pl->ndim; ++d) {
+      auto* tb = reinterpret_cast<DimTables<T>*>(pl->tables[d]);
+      allp = allp && tb->pow2 && (tb->four || tb->tw);
+    }
+    if (allp) return exec_pow2<T>(pl, in, out, dir);
+  }
   cudaStream_t st = current_stream();
   FFB_REQUIRE(st, FFB_ECUDA, "no CUDA stream (no device?)");
   const int nd = pl->ndim;
@@ -269,7 +427,7 @@ static int exec(ffb_plan* pl, const void* in, void* out, int dir) {
     // forward: x (r2c) into `out`, then y, z in place on `out`
     cx<T>* dst = reinterpret_cast<cx<T>*>(out);
     if (tb0->pow2) {
-      int rc = pow2_pass<T>(N0, R2C_ROWS, -1, in, dst, 1, N0, 0, 1, nkr, 0, rows, 1, T(1), tb0, st);
+      int rc = pow2_pass<T>(N0, R2C_ROWS, -1, in, dst, 1, N0, 0, 1, nkr, 0, rows, 1, T(1), tb0->tw, tb0->twr, st);
       if (rc) return rc;
     } else {
       int rc = ensure_ws(pl, 3);
@@ -297,7 +455,7 @@ static int exec(ffb_plan* pl, const void* in, void* out, int dir) {
     // scratch index 2 (generic) or 0 (pow2-only plans) holds the partially transformed spectrum
     cx<T>* w = reinterpret_cast<cx<T>*>(pl->ws[tb0->pow2 ? 0 : 2]);
     bool all_pow2 = true;
-    for (int d = 1; d < nd; ++d) all_pow2 = all_pow2 && reinterpret_cast<DimTables<T>*>(pl->tables[d])->pow2;
+    for (int d = 1; d < nd; ++d) { auto* tbd = reinterpret_cast<DimTables<T>*>(pl->tables[d]); all_pow2 = all_pow2 && tbd->pow2 && tbd->tw; }
     if (!all_pow2 && tb0->pow2) {  // generic y/z passes need ws[0], ws[1] as their own scratch
       rc = ensure_ws(pl, 3);
       if (rc) return rc;
@@ -309,7 +467,7 @@ static int exec(ffb_plan* pl, const void* in, void* out, int dir) {
     }
     spec = w;
   }
-  if (tb0->pow2) return pow2_pass<T>(N0, C2R_ROWS, +1, spec, out, 1, nkr, 0, 1, N0, 0, rows, 1, inv, tb0, st);
+  if (tb0->pow2) return pow2_pass<T>(N0, C2R_ROWS, +1, spec, out, 1, nkr, 0, 1, N0, 0, rows, 1, inv, tb0->tw, tb0->twr, st);
   int rc = ensure_ws(pl, 3);
   if (rc) return rc;
   // generic x: pre-process into ws[2]... but ws[2] may hold `spec`; use ws[0] for Z and route the axis scratch via ws[1]/out
@@ -353,11 +511,11 @@ static int exec_dist(ffb_plan* pl, const void* in, void* out, int dir) {
   if (dir < 0) {
     cx<T>* spec = reinterpret_cast<cx<T>*>(out);
     // x: real (nx, ny, nzl) -> w0 (nkr, ny, nzl)
-    if ((rc = pow2_pass<T>(N0, R2C_ROWS, -1, in, w0, 1, N0, 0, 1, nkr, 0, ny * nzl, 1, T(1), tb0, st))) return rc;
+    if ((rc = pow2_pass<T>(N0, R2C_ROWS, -1, in, w0, 1, N0, 0, 1, nkr, 0, ny * nzl, 1, T(1), tb0->tw, tb0->twr, st))) return rc;
     for (int c = 0; c < nch; ++c) {
       // y on z-chunk c: w0 -> w1 laid out [peer][kx, y_local, z_local]
-      if ((rc = pow2_pass<T>((int)ny, C2C_COLS, -1, w0 + c * zc * nkr * ny, w1 + c * sub, nkr, 1, nkr * ny, nkr, 1, nkr * nyl, nkr, zc, T(1), tb1,
-                             st, SegStride(), seg))) return rc;
+      if ((rc = pow2_pass<T>((int)ny, C2C_COLS, -1, w0 + c * zc * nkr * ny, w1 + c * sub, nkr, 1, nkr * ny, nkr, 1, nkr * nyl, nkr, zc, T(1), tb1->tw,
+                             nullptr, st, SegStride(), seg))) return rc;
       cudaEvent_t e = dist_next_event(d);
       FFB_CUDA(cudaEventRecord(e, st));
       FFB_CUDA(cudaStreamWaitEvent(d->comm_stream, e, 0));
@@ -368,11 +526,11 @@ static int exec_dist(ffb_plan* pl, const void* in, void* out, int dir) {
     FFB_CUDA(cudaEventRecord(e, d->comm_stream));
     FFB_CUDA(cudaStreamWaitEvent(st, e, 0));
     // z on the local y-slab, in place: (nkr*nyl) columns of length nz
-    return pow2_pass<T>((int)nz, C2C_COLS, -1, spec, spec, nkr * nyl, 1, 0, nkr * nyl, 1, 0, nkr * nyl, 1, T(1), tb2, st);
+    return pow2_pass<T>((int)nz, C2C_COLS, -1, spec, spec, nkr * nyl, 1, 0, nkr * nyl, 1, 0, nkr * nyl, 1, T(1), tb2->tw, nullptr, st);
   }
   // inverse
   const cx<T>* spec = reinterpret_cast<const cx<T>*>(in);
-  if ((rc = pow2_pass<T>((int)nz, C2C_COLS, +1, spec, w0, nkr * nyl, 1, 0, nkr * nyl, 1, 0, nkr * nyl, 1, T(1), tb2, st))) return rc;
+  if ((rc = pow2_pass<T>((int)nz, C2C_COLS, +1, spec, w0, nkr * nyl, 1, 0, nkr * nyl, 1, 0, nkr * nyl, 1, T(1), tb2->tw, nullptr, st))) return rc;
   cudaEvent_t e0 = dist_next_event(d);
   FFB_CUDA(cudaEventRecord(e0, st));
   FFB_CUDA(cudaStreamWaitEvent(d->comm_stream, e0, 0));
@@ -383,11 +541,11 @@ static int exec_dist(ffb_plan* pl, const void* in, void* out, int dir) {
     FFB_CUDA(cudaEventRecord(e, d->comm_stream));
     FFB_CUDA(cudaStreamWaitEvent(st, e, 0));
     // y on z-chunk c: w1 [peer][kx, y_local, z_local] -> w2 (nkr, ny, zc)
-    if ((rc = pow2_pass<T>((int)ny, C2C_COLS, +1, w1 + c * sub, w2 + c * zc * nkr * ny, nkr, 1, nkr * nyl, nkr, 1, nkr * ny, nkr, zc, T(1), tb1, st,
+    if ((rc = pow2_pass<T>((int)ny, C2C_COLS, +1, w1 + c * sub, w2 + c * zc * nkr * ny, nkr, 1, nkr * nyl, nkr, 1, nkr * ny, nkr, zc, T(1), tb1->tw, nullptr, st,
                            seg, SegStride()))) return rc;
     // x c2r on z-chunk c
     if ((rc = pow2_pass<T>(N0, C2R_ROWS, +1, w2 + c * zc * nkr * ny, reinterpret_cast<cx<T>*>(out) + c * zc * (long long)N0 * ny, 1, nkr, 0, 1, N0, 0,
-                           ny * zc, 1, inv, tb0, st))) return rc;
+                           ny * zc, 1, inv, tb0->tw, tb0->twr, st))) return rc;
   }
   // the next call may overwrite w0 / w1 on the compute stream: all exchanges above have been waited for already
   return FFB_OK;
@@ -433,7 +591,7 @@ int ffb_plan_create_dist(ffb_plan** out, int ndim, const int64_t* n, int dtype, 
   if (rc) return rc;
   ffb_plan* pl = *out;
   for (int d = 0; d < 3; ++d) {
-    const bool ok = dtype == FFB_F64 ? reinterpret_cast<DimTables<double>*>(pl->tables[d])->pow2 : reinterpret_cast<DimTables<float>*>(pl->tables[d])->pow2;
+    const bool ok = dtype == FFB_F64 ? (reinterpret_cast<DimTables<double>*>(pl->tables[d])->tw != nullptr) : (reinterpret_cast<DimTables<float>*>(pl->tables[d])->tw != nullptr);
     if (!ok) { ffb_plan_destroy(pl); *out = nullptr; return set_error(FFB_EUNSUPPORTED, "slab-decomposed plans need power-of-two sizes within the register-kernel range"); }
   }
   pl->dist = dist;

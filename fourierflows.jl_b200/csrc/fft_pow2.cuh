@@ -21,7 +21,9 @@
 
 namespace ffb {
 
-enum FftMode { C2C_ROWS = 0, C2C_COLS = 1, R2C_ROWS = 2, C2R_ROWS = 3 };
+// C2C_COLS_TW: first half of a four-step transform of a long strided line (N = N1*N2): length-N1 sub-transform over n1
+// for fixed n2 (= blockIdx.y % outer_mod), output k1 multiplied by the inter-pass twiddle exp(-/+2*pi*i*n2*k1/N).
+enum FftMode { C2C_ROWS = 0, C2C_COLS = 1, R2C_ROWS = 2, C2R_ROWS = 3, C2C_COLS_TW = 4 };
 
 template <typename T>
 struct Pow2Params {
@@ -33,6 +35,11 @@ struct Pow2Params {
   // so a pass can read / write destination-rank-major blocks without a pack kernel.  Unsegmented: mask = ~0, shift = 31.
   int in_seg_mask, in_seg_shift, out_seg_mask, out_seg_shift;
   long long in_seg_stride, out_seg_stride;
+  // two-level outer index: blockIdx.y = o -> (o % outer_mod)*os + (o / outer_mod)*os2   (outer_mod = 1<<30 when unused)
+  int outer_mod;
+  long long in_os2, out_os2;
+  const cx<T>* twN;                  // C2C_COLS_TW: exp(-2*pi*i*q/Nfull), q < Nfull
+  int twN_mask;                      // Nfull - 1
   long long nlines;                  // lines per outer index
   int W;                             // lines per CTA
   T scale;                           // applied to the output when != 1 (inverse normalisation)
@@ -172,7 +179,7 @@ template <typename T, int DIR, int MODE, int MAXT, int MINB, int R, int... Rs>
 __global__ void __launch_bounds__(MAXT, MINB) fft_pow2_kernel(const Pow2Params<T> p) {
   constexpr int N = radix_product<Rs...>::value;
   constexpr int Tn = N / R;
-  constexpr bool COLS = (MODE == C2C_COLS);
+  constexpr bool COLS = (MODE == C2C_COLS || MODE == C2C_COLS_TW);
   static_assert(N % R == 0, "R must divide N");
   using XW = typename xword<T>::type;
   extern __shared__ __align__(16) unsigned char ffb_smem[];
@@ -184,13 +191,14 @@ __global__ void __launch_bounds__(MAXT, MINB) fft_pow2_kernel(const Pow2Params<T
   const int t = COLS ? tid / W : tid % Tn;
   const long long line = (long long)blockIdx.x * W + w;
   const bool active = line < p.nlines;
-  const long long outer = blockIdx.y;
+  const int o_lo = (int)(blockIdx.y % (unsigned)p.outer_mod);
+  const long long o_hi = blockIdx.y / (unsigned)p.outer_mod;
 
   cx<T> v[R];
   // ---------------- load ----------------
   if constexpr (MODE == C2R_ROWS) {
     // Z[k] = (X[k] + conj(X[N-k])) + i*exp(+i*pi*k/N)*(X[k] - conj(X[N-k]))
-    const cx<T>* in = reinterpret_cast<const cx<T>*>(p.in) + outer * p.in_os + line * p.in_ls;
+    const cx<T>* in = reinterpret_cast<const cx<T>*>(p.in) + o_lo * p.in_os + o_hi * p.in_os2 + line * p.in_ls;
     const cx<T> wbase = load_tw<T, -1>(p.twr + t);
     static_for<0, R>([&](auto M) {
       constexpr int m = decltype(M)::value;
@@ -203,7 +211,7 @@ __global__ void __launch_bounds__(MAXT, MINB) fft_pow2_kernel(const Pow2Params<T
       v[m] = s + mul_i(wk * d);
     });
   } else {
-    const cx<T>* in = reinterpret_cast<const cx<T>*>(p.in) + outer * p.in_os + line * p.in_ls;
+    const cx<T>* in = reinterpret_cast<const cx<T>*>(p.in) + o_lo * p.in_os + o_hi * p.in_os2 + line * p.in_ls;
 #pragma unroll
     for (int m = 0; m < R; ++m) {
       const int i = t + m * Tn;
@@ -226,7 +234,7 @@ __global__ void __launch_bounds__(MAXT, MINB) fft_pow2_kernel(const Pow2Params<T
       if constexpr (PL == 2) xb[plane + addr(t + m * Tn)] = xget<T, 1>(v[m]);
     }
     __syncthreads();
-    cx<T>* out = reinterpret_cast<cx<T>*>(p.out) + outer * p.out_os + line * p.out_ls;
+    cx<T>* out = reinterpret_cast<cx<T>*>(p.out) + o_lo * p.out_os + o_hi * p.out_os2 + line * p.out_ls;
     const T half = T(0.5);
     const cx<T> wbase = load_tw<T, -1>(p.twr + t);
     static_for<0, R>([&](auto M) {
@@ -246,14 +254,23 @@ __global__ void __launch_bounds__(MAXT, MINB) fft_pow2_kernel(const Pow2Params<T
     });
   } else if constexpr (MODE == C2R_ROWS) {
     if (active) {
-      cx<T>* out = reinterpret_cast<cx<T>*>(p.out) + outer * p.out_os + line * p.out_ls;
+      cx<T>* out = reinterpret_cast<cx<T>*>(p.out) + o_lo * p.out_os + o_hi * p.out_os2 + line * p.out_ls;
       const T sc = p.scale;
 #pragma unroll
       for (int m = 0; m < R; ++m) stc(out + (t + m * Tn), sc * v[m]);
     }
   } else {
+    if constexpr (MODE == C2C_COLS_TW) {
+      // inter-pass twiddle of the four-step split: k1 = t + m*Tn, n2 = o_lo (same value for every column of the tile)
+#pragma unroll
+      for (int m = 1; m < R; ++m) {
+        const int q = (o_lo * (t + m * Tn)) & p.twN_mask;
+        v[m] = v[m] * load_tw<T, DIR>(p.twN + q);
+      }
+      if (t != 0) v[0] = v[0] * load_tw<T, DIR>(p.twN + ((o_lo * t) & p.twN_mask));
+    }
     if (active) {
-      cx<T>* out = reinterpret_cast<cx<T>*>(p.out) + outer * p.out_os + line * p.out_ls;
+      cx<T>* out = reinterpret_cast<cx<T>*>(p.out) + o_lo * p.out_os + o_hi * p.out_os2 + line * p.out_ls;
       const T sc = p.scale;
       auto off = [&](int i) { return (long long)(i & p.out_seg_mask) * p.out_es + (long long)(i >> p.out_seg_shift) * p.out_seg_stride; };
       if (sc != T(1)) {
