@@ -27,6 +27,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+FUSED = 1           # fold calcN!'s spectral multiplies / products / dealias into the FFT passes (--no-fuse disables)
 NVLINK_GBS = 770.0  # measured peer copy per direction per GPU (B200_PROFILING.md)
 
 
@@ -67,7 +68,7 @@ class Vorticity2D:
         return 4 * calcN + stages, fft, 0.0
 
     def make_gpu(self, ff, fo, rank, comm):
-        prob = ff.CProblem(self.shape, 2 * np.pi, stepper="ETDRK4", dt=self.dt, calcN="vorticity2d", nu=self.nu, T=self.T)
+        prob = ff.CProblem(self.shape, 2 * np.pi, stepper="ETDRK4", dt=self.dt, calcN="vorticity2d", nu=self.nu, T=self.T, fused=FUSED)
         prob.set_physical(fo.random_phase_field(self.shape, 2 * np.pi, self.K0, slope=-1.0, seed=1234 + rank))
         return prob
 
@@ -321,7 +322,8 @@ def run_gpu(args):
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak" if world > 1 else "strong", "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic",
         "config": {"workload": wl.name, "grid": list(wl.shape), "stepper": "ETDRK4", "parallelism": wl.parallelism,
-                   "l2": "every array is far larger than the 126 MB L2; no flush needed", "device_bytes_per_gpu": dev_bytes},
+                   "l2": "every array is far larger than the 126 MB L2; no flush needed", "device_bytes_per_gpu": dev_bytes,
+                   "calcN_fusion": bool(FUSED) and world == 1},
         "step_roofline": {"algorithmic_hbm_bytes_per_step": total_bytes, "nvlink_bytes_per_gpu_per_step": nvlink_bytes,
                           "hbm_ms_at_peak": hbm_ms, "nvlink_ms_at_770": nvl_ms, "ms_at_roofline_overlapped": max(hbm_ms, nvl_ms),
                           "frac": max(hbm_ms, nvl_ms) / ms_per_step, "frac_non_overlapped": (hbm_ms + nvl_ms) / ms_per_step,
@@ -358,7 +360,10 @@ def main():
     ap.add_argument("--nz-per-gpu", type=int, default=256, help="C5 z-planes per GPU (weak scaling; 256 x 8 = 2048)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="grid size of the cpu_baseline sample (default 4096 for C3)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fuse", action="store_true", help="run calcN! as separate elementwise kernels (the byte model of SURVEY 8d)")
     args = ap.parse_args()
+    global FUSED
+    FUSED = 0 if args.no_fuse else 1
     if args.impl == "reference":
         run_reference(args)
     else:

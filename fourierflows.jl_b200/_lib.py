@@ -42,6 +42,12 @@ class ffb_desc(C.Structure):
                 ("alias_hi", C.c_int32 * 3)]
 
 
+class ffb_fuse(C.Structure):
+    _fields_ = [("cr", C.c_double), ("ci", C.c_double), ("kx", C.c_void_p), ("l", C.c_void_p), ("m", C.c_void_p), ("w", C.c_void_p),
+                ("acc", C.c_void_p), ("ar", C.c_double), ("ai", C.c_double), ("akx", C.c_void_p), ("al", C.c_void_p), ("am", C.c_void_p),
+                ("dealias", C.c_int), ("alias_lo", C.c_int32 * 3), ("alias_hi", C.c_int32 * 3), ("mul", C.c_void_p)]
+
+
 CALCN_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p)
 
 
@@ -82,6 +88,8 @@ SIGNATURES = {
     "ffb_plan_describe": [_vp, C.c_char_p, _sz],
     "ffb_fft_forward": [_vp, _vp, _vp],
     "ffb_fft_inverse": [_vp, _vp, _vp],
+    "ffb_fft_forward_ex": [_vp, _vp, _vp, _P(ffb_fuse)],
+    "ffb_fft_inverse_ex": [_vp, _vp, _vp, _P(ffb_fuse)],
     "ffb_dist_unique_id": [_vp],
     "ffb_dist_init": [_P(_vp), _i, _i, _vp],
     "ffb_dist_destroy": [_vp],

@@ -3,6 +3,7 @@
 // A d-dimensional transform is one 1-D pass per dimension (P + (2d-1) S bytes of HBM traffic for r2c / c2r).
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include <map>
 #include <string>
 #include <vector>
@@ -231,8 +232,12 @@ template <typename T>
 static int pow2_pass(int N, int mode, int dir, const void* in, void* out, long long in_es, long long in_ls, long long in_os,
                      long long out_es, long long out_ls, long long out_os, long long nlines, long long nouter, T scale,
                      const cx<T>* tw, const cx<T>* twr, cudaStream_t st, SegStride in_seg = SegStride(), SegStride out_seg = SegStride(),
-                     Outer2 o2 = Outer2(), const cx<T>* twN = nullptr, int twN_mask = 0) {
+                     Outer2 o2 = Outer2(), const cx<T>* twN = nullptr, int twN_mask = 0,
+                     const typename Pow2Params<T>::Fuse* pro = nullptr, const typename Pow2Params<T>::Fuse* epi = nullptr, const T* rmul = nullptr) {
   Pow2Params<T> p;
+  if (pro) p.pro = *pro; else p.pro.on = 0;
+  if (epi) p.epi = *epi; else p.epi.on = 0;
+  p.rmul = rmul;
   p.in_seg_mask = in_seg.seg ? in_seg.seg - 1 : 0x7fffffff; p.in_seg_shift = in_seg.seg ? ilog2((uint64_t)in_seg.seg) : 31;
   p.in_seg_stride = in_seg.stride;
   p.out_seg_mask = out_seg.seg ? out_seg.seg - 1 : 0x7fffffff; p.out_seg_shift = out_seg.seg ? ilog2((uint64_t)out_seg.seg) : 31;
@@ -267,6 +272,9 @@ static int pow2_pass(int N, int mode, int dir, const void* in, void* out, long l
       const long long cnt = std::min<long long>(hchunk, o2.nhi - h0);
       p.in = reinterpret_cast<const cx<T>*>(in) + h0 * o2.in_os2;
       p.out = reinterpret_cast<cx<T>*>(out) + h0 * o2.out_os2;
+      if (pro && pro->w) p.pro.w = pro->w + h0 * o2.in_os2;
+      if (epi && epi->w) p.epi.w = epi->w + h0 * o2.out_os2;
+      if (epi && epi->acc) p.epi.acc = epi->acc + h0 * o2.out_os2;
       int rc = call_pow2<T>(N, mode, dir, p, (int)gx, (int)(cnt * o2.mod), threads, smem, st);
       if (rc) return rc;
     }
@@ -277,6 +285,11 @@ static int pow2_pass(int N, int mode, int dir, const void* in, void* out, long l
     const long long cnt = std::min<long long>(65535, nouter - o0);
     p.in = reinterpret_cast<const cx<T>*>(in) + o0 * in_os;
     p.out = reinterpret_cast<cx<T>*>(out) + o0 * out_os;
+    if (pro && pro->w) p.pro.w = pro->w + o0 * in_os;
+    if (epi && epi->w) p.epi.w = epi->w + o0 * out_os;
+    if (epi && epi->acc) p.epi.acc = epi->acc + o0 * out_os;
+    if (pro || epi) FFB_REQUIRE(nouter <= 65535 || (!(pro && pro->ko) && !(epi && (epi->ko || epi->ao || epi->loo > 0))), FFB_EUNSUPPORTED,
+                                "fused pass with more than 65535 outer slices");
     int rc = call_pow2<T>(N, mode, dir, p, (int)gx, (int)cnt, threads, smem, st);
     if (rc) return rc;
   }
@@ -287,22 +300,56 @@ static int pow2_pass(int N, int mode, int dir, const void* in, void* out, long l
 // (strictly out of place).  part: 0 = single pass, 1 = four-step A, 2 = four-step B.
 template <typename T>
 static int cols_pass(const DimTables<T>* tb, int part, long long inner, long long outer, const cx<T>* src, cx<T>* dst, int dir, T scale,
-                     cudaStream_t st) {
+                     cudaStream_t st, typename Pow2Params<T>::Fuse* pro = nullptr, typename Pow2Params<T>::Fuse* epi = nullptr) {
   const int N = tb->N;
-  if (part == 0)
-    return pow2_pass<T>(N, C2C_COLS, dir, src, dst, inner, 1, inner * N, inner, 1, inner * N, inner, outer, scale, tb->tw, nullptr, st);
+  if (part == 0) {
+    // single pass: transform index = t + m*Tn, the outer slice index is o_lo
+    if (pro) { pro->idm = 1; pro->ido = 0; if (pro->other_from_col == 0) pro->other_from_col = 2; }
+    if (epi) { epi->idm = 1; epi->ido = 0; if (epi->other_from_col == 0) epi->other_from_col = 2; }
+    return pow2_pass<T>(N, C2C_COLS, dir, src, dst, inner, 1, inner * N, inner, 1, inner * N, inner, outer, scale, tb->tw, nullptr, st,
+                        SegStride(), SegStride(), Outer2(), nullptr, 0, pro, epi);
+  }
   const int N1 = tb->N1, N2 = tb->N2;
   Outer2 o2;
   o2.nhi = outer; o2.in_os2 = inner * N; o2.out_os2 = inner * N;
   if (part == 1) {  // length-N1 transforms over n1 (element stride N2*inner) for each n2, times exp(-/+2 pi i n2 k1/N)
     o2.mod = N2;
+    if (pro) { pro->idm = N2; pro->ido = 1; }   // input index n = N2*n1 + n2
+    FFB_REQUIRE(!epi, FFB_EINVAL, "internal: epilogue on the first four-step sub-pass");
     return pow2_pass<T>(N1, C2C_COLS_TW, dir, src, dst, (long long)N2 * inner, 1, inner, (long long)N2 * inner, 1, inner, inner, N2, T(1), tb->tw1,
-                        nullptr, st, SegStride(), SegStride(), o2, tb->twN, N - 1);
+                        nullptr, st, SegStride(), SegStride(), o2, tb->twN, N - 1, pro, nullptr);
   }
+  if (epi) { epi->idm = N1; epi->ido = 1; }     // output index k = k1 + N1*k2
+  FFB_REQUIRE(!pro, FFB_EINVAL, "internal: prologue on the second four-step sub-pass");
   // length-N2 transforms over n2 (stride inner) for each k1 (outer stride N2*inner); output index k1 + N1*k2
   o2.mod = N1;
   return pow2_pass<T>(N2, C2C_COLS, dir, src, dst, inner, 1, (long long)N2 * inner, (long long)N1 * inner, 1, inner, inner, N1, scale, tb->tw2, nullptr,
-                      st, SegStride(), SegStride(), o2);
+                      st, SegStride(), SegStride(), o2, nullptr, 0, nullptr, epi);
+}
+
+// public ffb_fuse -> kernel hook for the strided pass along dimension d of a (e0, e1, e2) spectral array
+template <typename T>
+static typename Pow2Params<T>::Fuse make_hook(const ffb_fuse* f, int d, int nd, const long long e[3], bool epilogue) {
+  typename Pow2Params<T>::Fuse h;
+  memset(&h, 0, sizeof(h));
+  h.on = 1;
+  h.cr = (T)f->cr; h.ci = (T)f->ci;
+  const void* vec[3] = {f->kx, f->l, f->m};
+  const void* avec[3] = {f->akx, f->al, f->am};
+  const int other = (nd == 3) ? (d == 1 ? 2 : 1) : -1;
+  h.k0 = (const T*)vec[0]; h.kt = (const T*)vec[d]; h.ko = other >= 0 ? (const T*)vec[other] : nullptr;
+  h.w = (const T*)f->w;
+  h.n0 = (int)e[0];
+  h.other_from_col = (nd == 3 && d == 2) ? 1 : 0;   // z-pass: other = y = col / n0; y-pass: other = z = outer slice
+  if (epilogue) {
+    h.acc = (const cx<T>*)f->acc; h.ar = (T)f->ar; h.ai = (T)f->ai;
+    h.a0 = (const T*)avec[0]; h.at = (const T*)avec[d]; h.ao = other >= 0 ? (const T*)avec[other] : nullptr;
+    h.dealias = f->dealias;
+    h.lo0 = f->alias_lo[0]; h.hi0 = f->alias_hi[0];
+    h.lot = f->alias_lo[d]; h.hit = f->alias_hi[d];
+    if (other >= 0) { h.loo = f->alias_lo[other]; h.hio = f->alias_hi[other]; }
+  }
+  return h;
 }
 
 // c2c pass along dimension d of a dense complex array with extents e[0..2] x nb (x fastest).
@@ -330,7 +377,7 @@ static int c2c_dim(ffb_plan* pl, int d, const long long e[3], long long nb, cons
 // is scheduled over {IN (never written), OUT, WS0, WS1} so that the result lands in OUT and strictly out-of-place passes
 // (r2c, c2r, four-step B) never alias.
 template <typename T>
-static int exec_pow2(ffb_plan* pl, const void* in, void* out, int dir) {
+static int exec_pow2(ffb_plan* pl, const void* in, void* out, int dir, const ffb_fuse* fuse = nullptr) {
   cudaStream_t st = current_stream();
   FFB_REQUIRE(st, FFB_ECUDA, "no CUDA stream (no device?)");
   const int nd = pl->ndim;
@@ -366,6 +413,11 @@ static int exec_pow2(ffb_plan* pl, const void* in, void* out, int dir) {
   auto* tb0 = reinterpret_cast<DimTables<T>*>(pl->tables[0]);
   long long rows = nb;
   for (int d = 1; d < nd; ++d) rows *= pl->n[d];
+  if (fuse) {
+    FFB_REQUIRE(pl->kind == FFB_R2C && nd >= 2 && nb == 1, FFB_EUNSUPPORTED, "fused transforms need an r2c plan with ndim >= 2 and one field");
+    FFB_REQUIRE(dir > 0 ? ops[0].kind == 3 : ops[n - 1].kind == 3, FFB_EUNSUPPORTED, "no strided pass to fuse into");
+  }
+  const bool want_pro = fuse && dir > 0 && (fuse->kx || fuse->l || fuse->m || fuse->w || fuse->cr != 1.0 || fuse->ci != 0.0);
   for (int i = 0; i < n; ++i) {
     const Op& op = ops[i];
     const void* s_ = buf(src[i]);
@@ -374,13 +426,20 @@ static int exec_pow2(ffb_plan* pl, const void* in, void* out, int dir) {
     int rc;
     if (op.kind == 0) rc = pow2_pass<T>(tb0->N, C2C_ROWS, dir, s_, d_, 1, tb0->N, 0, 1, tb0->N, 0, rows, 1, sc, tb0->tw, nullptr, st);
     else if (op.kind == 1) rc = pow2_pass<T>(tb0->N, R2C_ROWS, -1, s_, d_, 1, tb0->N, 0, 1, e[0], 0, rows, 1, T(1), tb0->tw, tb0->twr, st);
-    else if (op.kind == 2) rc = pow2_pass<T>(tb0->N, C2R_ROWS, +1, s_, d_, 1, e[0], 0, 1, tb0->N, 0, rows, 1, sc, tb0->tw, tb0->twr, st);
+    else if (op.kind == 2)
+      rc = pow2_pass<T>(tb0->N, C2R_ROWS, +1, s_, d_, 1, e[0], 0, 1, tb0->N, 0, rows, 1, sc, tb0->tw, tb0->twr, st, SegStride(), SegStride(), Outer2(),
+                        nullptr, 0, nullptr, nullptr, fuse ? reinterpret_cast<const T*>(fuse->mul) : nullptr);
     else {
       long long inner = 1, outer = nb;
       for (int q = 0; q < op.d; ++q) inner *= e[q];
       for (int q = op.d + 1; q < 3; ++q) outer *= e[q];
+      typename Pow2Params<T>::Fuse hook;
+      typename Pow2Params<T>::Fuse* pro = nullptr;
+      typename Pow2Params<T>::Fuse* epi = nullptr;
+      if (want_pro && i == 0) { hook = make_hook<T>(fuse, op.d, nd, e, false); pro = &hook; }
+      if (fuse && dir < 0 && i == n - 1) { hook = make_hook<T>(fuse, op.d, nd, e, true); epi = &hook; }
       rc = cols_pass<T>(reinterpret_cast<DimTables<T>*>(pl->tables[op.d]), op.part, inner, outer, reinterpret_cast<const cx<T>*>(s_),
-                        reinterpret_cast<cx<T>*>(d_), dir, sc, st);
+                        reinterpret_cast<cx<T>*>(d_), dir, sc, st, pro, epi);
     }
     if (rc) return rc;
   }
@@ -635,6 +694,22 @@ int ffb_fft_forward(ffb_plan* pl, const void* in, void* out) {
   if (pl->dist) return pl->dtype == FFB_F64 ? exec_dist<double>(pl, in, out, -1) : exec_dist<float>(pl, in, out, -1);
   return pl->dtype == FFB_F64 ? exec<double>(pl, in, out, -1) : exec<float>(pl, in, out, -1);
 }
+
+static int exec_fused(ffb_plan* pl, const void* in, void* out, int dir, const ffb_fuse* fuse) {
+  FFB_REQUIRE(pl && in && out && fuse, FFB_EINVAL, "NULL argument");
+  FFB_REQUIRE(in != out, FFB_EINVAL, "fused transforms are out of place");
+  FFB_REQUIRE(!pl->dist, FFB_EUNSUPPORTED, "fused transforms on slab-decomposed plans are not implemented");
+  bool allp = true;
+  for (int d = 0; d < pl->ndim; ++d) {
+    if (pl->dtype == FFB_F64) { auto* tb = reinterpret_cast<DimTables<double>*>(pl->tables[d]); allp = allp && tb->pow2 && (tb->four || tb->tw); }
+    else { auto* tb = reinterpret_cast<DimTables<float>*>(pl->tables[d]); allp = allp && tb->pow2 && (tb->four || tb->tw); }
+  }
+  FFB_REQUIRE(allp, FFB_EUNSUPPORTED, "fused transforms need power-of-two sizes");
+  return pl->dtype == FFB_F64 ? exec_pow2<double>(pl, in, out, dir, fuse) : exec_pow2<float>(pl, in, out, dir, fuse);
+}
+
+int ffb_fft_forward_ex(ffb_plan* pl, const void* in, void* out, const ffb_fuse* fuse) { return exec_fused(pl, in, out, -1, fuse); }
+int ffb_fft_inverse_ex(ffb_plan* pl, const void* in, void* out, const ffb_fuse* fuse) { return exec_fused(pl, in, out, +1, fuse); }
 
 int ffb_fft_inverse(ffb_plan* pl, const void* in, void* out) {
   FFB_REQUIRE(pl && in && out, FFB_EINVAL, "NULL argument");

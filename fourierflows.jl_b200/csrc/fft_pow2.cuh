@@ -38,6 +38,21 @@ struct Pow2Params {
   // two-level outer index: blockIdx.y = o -> (o % outer_mod)*os + (o / outer_mod)*os2   (outer_mod = 1<<30 when unused)
   int outer_mod;
   long long in_os2, out_os2;
+  // Fused elementwise work (north star: spectral multiplies, products and the dealias mask folded into the passes).
+  // Coordinates of an element of a strided pass: i0 = col % n0 (kx index), it = transform index
+  // (= idm*(t + m*N/16) + ido*o_lo), io = "other" index (col / n0 for a z-pass, o_hi for a y-pass).
+  struct Fuse {
+    int on;                      // 0 = none
+    T cr, ci;                    // complex scalar
+    const T* k0; const T* kt; const T* ko;   // optional wavenumber factors by i0 / it / io
+    const T* w;                  // optional dense real factor, same layout as the array (pre-offset like in / out)
+    const cx<T>* acc;            // epilogue only: out = f*own + g*acc[idx]
+    T ar, ai; const T* a0; const T* at; const T* ao;
+    int dealias; int lo0, hi0, lot, hit, loo, hio;   // 1-based inclusive alias ranges on i0 / it / io (lo = 0: none)
+    int n0, idm, ido, other_from_col;   // other_from_col: 0 = o_hi, 1 = col / n0, 2 = o_lo
+  };
+  Fuse pro, epi;
+  const T* rmul;                     // C2R_ROWS: real result multiplied by this real field (same layout as out)
   const cx<T>* twN;                  // C2C_COLS_TW: exp(-2*pi*i*q/Nfull), q < Nfull
   int twN_mask;                      // Nfull - 1
   long long nlines;                  // lines per outer index
@@ -175,6 +190,17 @@ template <typename T> FFB_D void stc(cx<T>* p, cx<T> c) {
   __stcs(reinterpret_cast<V*>(p), q);
 }
 
+// factor (cr + i ci) * k0[i0] * kt[it] * ko[io] * w[off], evaluated left to right like `im * kr * invKrsq * sol`
+template <typename T>
+FFB_D cx<T> fuse_factor(T cr, T ci, const T* k0, const T* kt, const T* ko, const T* w, int i0, int it, long long io, long long off) {
+  T fr = cr, fi = ci;
+  if (k0) { const T v = __ldg(k0 + i0); fr *= v; fi *= v; }
+  if (kt) { const T v = __ldg(kt + it); fr *= v; fi *= v; }
+  if (ko) { const T v = __ldg(ko + io); fr *= v; fi *= v; }
+  if (w) { const T v = __ldcs(w + off); fr *= v; fi *= v; }
+  return mk<T>(fr, fi);
+}
+
 template <typename T, int DIR, int MODE, int MAXT, int MINB, int R, int... Rs>
 __global__ void __launch_bounds__(MAXT, MINB) fft_pow2_kernel(const Pow2Params<T> p) {
   constexpr int N = radix_product<Rs...>::value;
@@ -217,6 +243,17 @@ __global__ void __launch_bounds__(MAXT, MINB) fft_pow2_kernel(const Pow2Params<T
       const int i = t + m * Tn;
       v[m] = active ? ldc(in + (long long)(i & p.in_seg_mask) * p.in_es + (long long)(i >> p.in_seg_shift) * p.in_seg_stride) : mk<T>(0, 0);
     }
+    if (p.pro.on && active) {
+      const int i0 = (int)(line % p.pro.n0);
+      const long long io = p.pro.other_from_col == 1 ? line / p.pro.n0 : (p.pro.other_from_col == 2 ? (long long)o_lo : o_hi);
+      const long long base = (in - reinterpret_cast<const cx<T>*>(p.in));
+#pragma unroll
+      for (int m = 0; m < R; ++m) {
+        const int i = t + m * Tn;
+        const long long off = base + (long long)(i & p.in_seg_mask) * p.in_es + (long long)(i >> p.in_seg_shift) * p.in_seg_stride;
+        v[m] = fuse_factor<T>(p.pro.cr, p.pro.ci, p.pro.k0, p.pro.kt, p.pro.ko, p.pro.w, i0, p.pro.idm * i + p.pro.ido * o_lo, io, off) * v[m];
+      }
+    }
   }
   // ---------------- transform ----------------
   run_passes<T, DIR, COLS, R, N, 1, 0, Rs...>(v, t, w, W, xb, p.tw);
@@ -256,8 +293,17 @@ __global__ void __launch_bounds__(MAXT, MINB) fft_pow2_kernel(const Pow2Params<T
     if (active) {
       cx<T>* out = reinterpret_cast<cx<T>*>(p.out) + o_lo * p.out_os + o_hi * p.out_os2 + line * p.out_ls;
       const T sc = p.scale;
+      if (p.rmul) {
+        const cx<T>* mulp = reinterpret_cast<const cx<T>*>(p.rmul) + o_lo * p.out_os + o_hi * p.out_os2 + line * p.out_ls;
 #pragma unroll
-      for (int m = 0; m < R; ++m) stc(out + (t + m * Tn), sc * v[m]);
+        for (int m = 0; m < R; ++m) {
+          const cx<T> z = ldc(mulp + (t + m * Tn));   // two consecutive reals of the multiplier field
+          stc(out + (t + m * Tn), mk<T>(sc * v[m].x * z.x, sc * v[m].y * z.y));
+        }
+      } else {
+#pragma unroll
+        for (int m = 0; m < R; ++m) stc(out + (t + m * Tn), sc * v[m]);
+      }
     }
   } else {
     if constexpr (MODE == C2C_COLS_TW) {
@@ -273,7 +319,26 @@ __global__ void __launch_bounds__(MAXT, MINB) fft_pow2_kernel(const Pow2Params<T
       cx<T>* out = reinterpret_cast<cx<T>*>(p.out) + o_lo * p.out_os + o_hi * p.out_os2 + line * p.out_ls;
       const T sc = p.scale;
       auto off = [&](int i) { return (long long)(i & p.out_seg_mask) * p.out_es + (long long)(i >> p.out_seg_shift) * p.out_seg_stride; };
-      if (sc != T(1)) {
+      if (p.epi.on) {
+        const int i0 = (int)(line % p.epi.n0);
+        const long long io = p.epi.other_from_col == 1 ? line / p.epi.n0 : (p.epi.other_from_col == 2 ? (long long)o_lo : o_hi);
+        const long long base = (out - reinterpret_cast<cx<T>*>(p.out));
+        const bool dead0 = p.epi.dealias && ((p.epi.lo0 > 0 && i0 >= p.epi.lo0 - 1 && i0 < p.epi.hi0) || (p.epi.loo > 0 && io >= p.epi.loo - 1 && io < p.epi.hio));
+#pragma unroll
+        for (int m = 0; m < R; ++m) {
+          const int i = t + m * Tn;
+          const int it = p.epi.idm * i + p.epi.ido * o_lo;
+          const long long o = off(i);
+          cx<T> r;
+          if (dead0 || (p.epi.dealias && p.epi.lot > 0 && it >= p.epi.lot - 1 && it < p.epi.hit)) {
+            r = mk<T>(0, 0);
+          } else {
+            r = fuse_factor<T>(p.epi.cr, p.epi.ci, p.epi.k0, p.epi.kt, p.epi.ko, p.epi.w, i0, it, io, base + o) * (sc * v[m]);
+            if (p.epi.acc) r = r + fuse_factor<T>(p.epi.ar, p.epi.ai, p.epi.a0, p.epi.at, p.epi.ao, (const T*)nullptr, i0, it, io, 0) * ldc(p.epi.acc + base + o);
+          }
+          stc(out + o, r);
+        }
+      } else if (sc != T(1)) {
 #pragma unroll
         for (int m = 0; m < R; ++m) stc(out + off(t + m * Tn), sc * v[m]);
       } else {

@@ -113,6 +113,26 @@ static int calcN_impl(ffb_problem* p, void* N, const void* sol, double t) {
       if ((rc = ffb_fft_forward(p->plan, p->ph1, p->sh1))) return rc;
       return ffb_ew_spectral_mul(N, p->sh1, 0.0, 1.0, p->kr, 1, nullptr, 0, nullptr, 0, nullptr, 0, 0, d);
     case FFB_CALCN_VORTICITY2D: {
+      if (p->cfg.fused) {
+        // Same equation with the elementwise work folded into the transforms (5 transforms, no separate kernels):
+        //   zeta = irfft(sol);  u*zeta = irfft(im*l*invKrsq .* sol) .* zeta;  v*zeta = irfft(-im*kr*invKrsq .* sol) .* zeta
+        //   uh = rfft(u*zeta);  N = dealias!(-im*kr .* uh - im*l .* rfft(v*zeta))
+        ffb_fuse f;
+        memset(&f, 0, sizeof(f));
+        f.cr = 1.0;
+        if ((rc = ffb_fft_inverse(p->plan, sol, p->ph3))) return rc;
+        f.cr = 0.0; f.ci = 1.0; f.l = p->l; f.w = p->invKrsq; f.mul = p->ph3;
+        if ((rc = ffb_fft_inverse_ex(p->plan, sol, p->ph1, &f))) return rc;
+        f.ci = -1.0; f.l = nullptr; f.kx = p->kr;
+        if ((rc = ffb_fft_inverse_ex(p->plan, sol, p->ph2, &f))) return rc;
+        if ((rc = ffb_fft_forward(p->plan, p->ph1, p->sh1))) return rc;
+        memset(&f, 0, sizeof(f));
+        f.cr = 0.0; f.ci = -1.0; f.l = p->l;                   // own term: -im * l * rfft(v*zeta)
+        f.acc = p->sh1; f.ar = 0.0; f.ai = -1.0; f.akx = p->kr;   // accumulated term: -im * kr * uh
+        f.dealias = 1;
+        for (int q = 0; q < 3; ++q) { f.alias_lo[q] = d->alias_lo[q]; f.alias_hi[q] = d->alias_hi[q]; }
+        return ffb_fft_forward_ex(p->plan, p->ph2, N, &f);
+      }
       const unsigned rows = (unsigned)d->dims[1];
       { ProfScope ps("calcN_vort_prep", 3.0 * p->sbytes + p->rbytes);
       vort_prep_kernel<T><<<rows, 256, 0, s>>>((cx<T>*)p->sh1, (cx<T>*)p->sh2, (const cx<T>*)sol, (const T*)p->invKrsq, (const T*)p->kr, (const T*)p->l, n0);
@@ -143,6 +163,13 @@ static int calcN_impl(ffb_problem* p, void* N, const void* sol, double t) {
       square_real_kernel<T><<<blocks, 256, 0, s>>>((T*)p->ph1, p->nphys);
       count_launch(); }
       FFB_CHECK_LAUNCH();
+      if (p->cfg.fused && !p->cfg.dist) {
+        ffb_fuse f;
+        memset(&f, 0, sizeof(f));
+        f.cr = 0.0; f.ci = -0.5; f.kx = p->kr; f.dealias = 1;
+        for (int q = 0; q < 3; ++q) { f.alias_lo[q] = d->alias_lo[q]; f.alias_hi[q] = d->alias_hi[q]; }
+        return ffb_fft_forward_ex(p->plan, p->ph1, N, &f);
+      }
       if ((rc = ffb_fft_forward(p->plan, p->ph1, p->sh1))) return rc;
       return ffb_ew_spectral_mul(N, p->sh1, 0.0, -0.5, p->kr, 1, nullptr, 0, nullptr, 0, nullptr, 0, 1, d);
     }

@@ -68,6 +68,34 @@ class Plan:
         L.call("ffb_fft_inverse", self._h, ah.ptr, out.ptr)
         return out
 
+    # fused forms (ffb_fft_forward_ex / ffb_fft_inverse_ex): spectral multiplies, products and dealias folded into the passes
+    @staticmethod
+    def _fuse(coef=1.0, kx=None, l=None, m=None, w=None, acc=None, acoef=0.0, akx=None, al=None, am=None, alias=None, mul=None):
+        f = L.ffb_fuse()
+        c, a = complex(coef), complex(acoef)
+        f.cr, f.ci, f.ar, f.ai = c.real, c.imag, a.real, a.imag
+        ptr = lambda x: x.ptr if x is not None else None
+        f.kx, f.l, f.m, f.w, f.acc, f.akx, f.al, f.am, f.mul = (ptr(v) for v in (kx, l, m, w, acc, akx, al, am, mul))
+        f.dealias = 1 if alias is not None else 0
+        al3 = list(alias) + [None] * (3 - len(alias)) if alias is not None else [None] * 3
+        f.alias_lo = (C.c_int32 * 3)(*[(r[0] if r else 0) for r in al3])
+        f.alias_hi = (C.c_int32 * 3)(*[(r[1] if r else 0) for r in al3])
+        return f
+
+    def ldiv_ex(self, out: DevArray, ah: DevArray, coef=1.0, kx=None, l=None, m=None, w=None, mul=None):
+        """`out = irfft((coef * kx * l * m * w) .* ah) .* mul` in one pass chain."""
+        f = self._fuse(coef=coef, kx=kx, l=l, m=m, w=w, mul=mul)
+        L.call("ffb_fft_inverse_ex", self._h, ah.ptr, out.ptr, C.byref(f))
+        return out
+
+    def mul_ex(self, out: DevArray, a: DevArray, coef=1.0, kx=None, l=None, m=None, w=None, acc=None, acoef=0.0, akx=None, al=None, am=None,
+               alias=None):
+        """`out = dealias!((coef * kx * l * m * w) .* rfft(a) + (acoef * akx * al * am) .* acc)`; `alias` = per-dimension
+        1-based ranges (kralias, lalias[, malias]) or None."""
+        f = self._fuse(coef=coef, kx=kx, l=l, m=m, w=w, acc=acc, acoef=acoef, akx=akx, al=al, am=am, alias=alias)
+        L.call("ffb_fft_forward_ex", self._h, a.ptr, out.ptr, C.byref(f))
+        return out
+
     def __mul__(self, a: DevArray):
         return self.mul(DevArray(self.spectral_shape, cxtype(self.T)), a)
 

@@ -107,6 +107,25 @@ int ffb_fft_forward(ffb_plan* plan, const void* in, void* out);
  * (the reference allows c2r to destroy it; preserving is a superset). */
 int ffb_fft_inverse(ffb_plan* plan, const void* in, void* out);
 
+/* Fused forms (SURVEY 8b B2 "optional fused forms"; north star: the linear-operator multiply, the dealias! mask and the
+ * physical-space products are folded into the FFT passes).  All-power-of-two plans with ndim >= 2 only.
+ *   inverse_ex:  out = irfft( F .* in ) .* mul       F[k,l,m] = (cr + i ci) * kx[k] * l[l] * m[m] * w[k,l,m]
+ *   forward_ex:  out = dealias!( F .* rfft(in) + G .* acc )   G = (ar + i ai) * akx[k] * al[l] * am[m]
+ * Any vector / array pointer may be NULL (factor 1).  `w`, `acc` have the layout of the spectral array, `mul` of the
+ * physical array.  dealias != 0 zeroes the alias box given by alias_lo/hi (as in ffb_desc). */
+typedef struct {
+  double cr, ci;
+  const void *kx, *l, *m, *w;
+  const void* acc;
+  double ar, ai;
+  const void *akx, *al, *am;
+  int dealias;
+  int32_t alias_lo[3], alias_hi[3];
+  const void* mul;
+} ffb_fuse;
+int ffb_fft_forward_ex(ffb_plan* plan, const void* in, void* out, const ffb_fuse* fuse);
+int ffb_fft_inverse_ex(ffb_plan* plan, const void* in, void* out, const ffb_fuse* fuse);
+
 /* ---------------------------------------------------------------- multi-GPU slab decomposition
  * No reference counterpart: FourierFlows.jl is single-device (README.md:58, docs/src/gpu.md:57); this is the new
  * capability named by BASELINE.json north_star.  One process per GPU; the caller (torch.distributed, MPI, ...) moves the

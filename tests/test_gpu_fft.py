@@ -194,3 +194,46 @@ def test_c2r_ignores_non_hermitian_parts_like_fftw(ff, shape):
     assert relerr(plan.solve(dev(ff, xh)).to_numpy(), ref) <= 1e-13
     gen = ff.Plan(shape, np.float64, ff._lib.FFB_R2C, flags=ff._lib.FFB_PLAN_FORCE_GENERIC)
     assert relerr(gen.solve(dev(ff, xh)).to_numpy(), ref) <= 1e-13
+
+
+@pytest.mark.parametrize("T,tol", [(np.float64, 1e-12), (np.float32, 1e-5)])
+@pytest.mark.parametrize("shape", [(64, 32), (128, 4096), (32, 16, 64)], ids=lambda s: "x".join(map(str, s)))
+def test_fused_transforms_match_unfused_reference_expressions(ff, shape, T, tol):
+    """ffb_fft_inverse_ex / ffb_fft_forward_ex (spectral factor, physical product, accumulate + dealias folded into the
+    passes) against the same expressions evaluated by the oracle; covers single-pass and four-step strided passes."""
+    nd = len(shape)
+    G = {2: ff.TwoDGrid, 3: ff.ThreeDGrid}[nd]
+    OG = {2: fo.TwoDGrid, 3: fo.ThreeDGrid}[nd]
+    kw = dict(nx=shape[0], Lx=2 * np.pi, ny=shape[1], Ly=3 * np.pi, T=T)
+    if nd == 3:
+        kw.update(nz=shape[2], Lz=4.0)
+    g, og = G(ff.GPU(), **kw), OG(**kw)
+    rng = np.random.default_rng(31)
+    sh = (g.nkr,) + tuple(shape[1:])
+    cT = np.complex64 if T == np.float32 else np.complex128
+    ah = np.asfortranarray((rng.standard_normal(sh) + 1j * rng.standard_normal(sh)).astype(cT))
+    zeta = np.asfortranarray(rng.standard_normal(shape).astype(T))
+    plan, oplan = g.rfftplan, og.rfftplan
+    # inverse_ex: irfft(im * l * invKrsq .* ah) .* zeta
+    ref = oplan.solve(((1j * og.l) * og.invKrsq) * ah) * zeta
+    out = ff.DevArray(shape, T)
+    plan.ldiv_ex(out, dev(ff, ah), coef=1j, l=g.l, w=g.invKrsq, mul=dev(ff, zeta))
+    assert relerr(out.to_numpy(), ref) <= tol
+    ref = oplan.solve(((-1j * og.kr) * og.invKrsq) * ah)
+    plan.ldiv_ex(out, dev(ff, ah), coef=-1j, kx=g.kr, w=g.invKrsq)
+    assert relerr(out.to_numpy(), ref) <= tol
+    # forward_ex: dealias!(-im*kr .* acc - im*l .* rfft(zeta))  (and the m-vector / malias in 3-D)
+    acc = np.asfortranarray((rng.standard_normal(sh) + 1j * rng.standard_normal(sh)).astype(cT))
+    ref = (-1j * og.kr) * acc - (1j * og.l) * (oplan * zeta)
+    ref = np.asfortranarray(ref)
+    fo.dealias(ref, og)
+    outh = ff.DevArray(sh, cT)
+    alias = [g.kralias, g.lalias] + ([g.malias] if nd == 3 else [])
+    plan.mul_ex(outh, dev(ff, zeta), coef=-1j, l=g.l, acc=dev(ff, acc), acoef=-1j, akx=g.kr, alias=alias)
+    assert relerr(outh.to_numpy(), ref) <= tol
+    assert np.array_equal(outh.to_numpy() == 0, ref == 0), "the dealiased box must be exactly zero"
+    if nd == 3:
+        ref = np.asfortranarray(((-0.5j * og.kr) * og.m) * (oplan * zeta))
+        fo.dealias(ref, og)
+        plan.mul_ex(outh, dev(ff, zeta), coef=-0.5j, kx=g.kr, m=g.m, alias=alias)
+        assert relerr(outh.to_numpy(), ref) <= tol

@@ -212,3 +212,26 @@ def test_diagnostics_bookkeeping(ff):
     ff.stepforward(prob, diag, 100)
     assert len(diag) == 51 and diag.steps[diag.i - 1] == 100
     assert np.isclose(diag[-1], e0 * np.exp(-2.0 * float(prob.clock.t)), rtol=1e-9)
+
+
+@pytest.mark.parametrize("n,stepper", [(64, "ETDRK4"), (128, "FilteredRK4")])
+def test_fused_c_driven_vorticity_matches_oracle(ff, n, stepper):
+    """`fused = 1`: the calcN! elementwise kernels folded into the FFT passes; same tolerance against the oracle"""
+    nu, dt = 1e-3, 2e-3
+    cp = ff.CProblem((n, n), 2 * np.pi, stepper=stepper, dt=dt, calcN="vorticity2d", nu=nu, fused=1)
+    oprob = fo.TwoDNavierStokes.Problem(nx=n, nu=nu, dt=dt, stepper=stepper)
+    z0 = fo.random_phase_field((n, n), 2 * np.pi, 8.0, slope=-1, seed=1234)
+    cp.set_physical(z0)
+    oprob.grid.rfftplan.mul(oprob.sol, z0)
+    for s in range(5):
+        cp.stepforward(1)
+        fo.stepforward(oprob, 1)
+        assert relerr(cp.sol.to_numpy(), oprob.sol) <= (s + 1) * 1e-12
+    cb = ff.CProblem((32, 32, 32), 2 * np.pi, stepper="FilteredRK4", dt=1e-3, calcN="burgers3d", nu=1e-3, fused=1)
+    ob = fo.Burgers3D.Problem(nx=32, kappa=1e-3, dt=1e-3, stepper="FilteredRK4")
+    c0 = fo.random_phase_field((32, 32, 32), 2 * np.pi, 4.0, slope=0)
+    cb.set_physical(c0)
+    ob.grid.rfftplan.mul(ob.sol, c0)
+    cb.stepforward(3)
+    fo.stepforward(ob, 3)
+    assert relerr(cb.sol.to_numpy(), ob.sol) <= 3e-12
