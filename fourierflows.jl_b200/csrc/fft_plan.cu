@@ -11,6 +11,8 @@
 #include "fft_pow2.cuh"
 #include "fft_pow2_dispatch.h"
 #include "dist.h"
+#include "fft_cluster.cuh"
+#include "fft_cluster_dispatch.h"
 
 namespace ffb {
 
@@ -60,6 +62,7 @@ struct DimTables {
   cx<T>* twr = nullptr;  // split step: exp(-i pi k / N), k <= N (dim 0 of R2C plans only)
   // four-step split of a long strided line: N = N1*N2, two short sub-passes with wide rows
   bool four = false;
+  bool cluster = false;  // one cluster (DSMEM) kernel instead of the two four-step sub-passes
   int N1 = 0, N2 = 0;
   cx<T>* tw1 = nullptr;  // base twiddles of the length-N1 sub-transform
   cx<T>* tw2 = nullptr;  // base twiddles of the length-N2 sub-transform
@@ -110,6 +113,14 @@ template <typename T> static int fourstep_min() {
   return sizeof(T) == 8 ? 4096 : 8192;
 }
 
+// Cluster (distributed shared memory) four-step kernel: one HBM round trip instead of two, transpose through DSMEM.
+// MEASURED SLOWER than the two-kernel four-step on B200 (N=8192 Float64: 639 us vs 414 us; DSMEM moves ~21 B/clk/SM,
+// about 6 TB/s aggregate, and the two cluster barriers serialise 8 CTAs), so it is opt-in: FFB_CLUSTER_MIN=<min N> enables.
+template <typename T> static int cluster_min() {
+  if (const char* e = getenv("FFB_CLUSTER_MIN")) { const int v = atoi(e); return v > 0 ? v : (1 << 30); }
+  return 1 << 30;
+}
+
 template <typename T>
 static int build_tables(ffb_plan* pl) {
   for (int d = 0; d < pl->ndim; ++d) {
@@ -122,9 +133,11 @@ static int build_tables(ffb_plan* pl) {
     const int np = pow2_radices(N, rad);
     const bool allow = !(pl->flags & FFB_PLAN_FORCE_GENERIC) && is_pow2((uint64_t)N) && N >= 2;
     tb->pow2 = allow && N <= pow2_max_n(sizeof(T)) && np > 0;
-    if (allow && d > 0 && N >= fourstep_min<T>() && N <= 65536) {
+    const bool use_cluster = allow && d > 0 && cluster_has(N) && N >= cluster_min<T>();
+    if (allow && d > 0 && ((N >= fourstep_min<T>() && N <= 65536) || use_cluster)) {
       const int l2 = ilog2((uint64_t)N);
       tb->four = true;
+      tb->cluster = use_cluster;
       tb->N1 = 1 << (l2 / 2);
       tb->N2 = N / tb->N1;
       tb->pow2 = true;
@@ -152,7 +165,8 @@ static int build_tables(ffb_plan* pl) {
       if (rc) return rc;
     }
     char buf[96];
-    if (tb->four) snprintf(buf, sizeof(buf), "dim%d:N=%d:pow2-four-step(%dx%d) ", d, N, tb->N1, tb->N2);
+    if (tb->cluster) snprintf(buf, sizeof(buf), "dim%d:N=%d:pow2-cluster-dsmem-four-step(%dx%d) ", d, N, tb->N1, tb->N2);
+    else if (tb->four) snprintf(buf, sizeof(buf), "dim%d:N=%d:pow2-four-step(%dx%d) ", d, N, tb->N1, tb->N2);
     else snprintf(buf, sizeof(buf), "dim%d:N=%d:%s ", d, N, tb->pow2 ? "pow2-register-stockham" : "generic-mixed-radix");
     pl->desc += buf;
   }
@@ -238,6 +252,14 @@ static int pow2_pass(int N, int mode, int dir, const void* in, void* out, long l
   if (pro) p.pro = *pro; else p.pro.on = 0;
   if (epi) p.epi = *epi; else p.epi.on = 0;
   p.rmul = rmul;
+  p.pf_ahead = 0;
+  if (mode == C2C_ROWS || mode == R2C_ROWS || mode == C2R_ROWS) {
+    // distance = one full wave of resident CTAs (tuning override: FFB_PF_AHEAD, 0 disables)
+    static int pf_env = -2;
+    if (pf_env == -2) { const char* e = getenv("FFB_PF_AHEAD"); pf_env = e ? atoi(e) : -1; }
+    // measured (tools/sweep3.py): +10 % for the Float64 r2c pass of 4096-point lines at one wave ahead, neutral or negative elsewhere
+    p.pf_ahead = pf_env >= 0 ? pf_env : ((mode == R2C_ROWS && N * sizeof(cx<T>) >= 32768) ? num_sms() : 0);
+  }
   p.in_seg_mask = in_seg.seg ? in_seg.seg - 1 : 0x7fffffff; p.in_seg_shift = in_seg.seg ? ilog2((uint64_t)in_seg.seg) : 31;
   p.in_seg_stride = in_seg.stride;
   p.out_seg_mask = out_seg.seg ? out_seg.seg - 1 : 0x7fffffff; p.out_seg_shift = out_seg.seg ? ilog2((uint64_t)out_seg.seg) : 31;
@@ -310,6 +332,32 @@ static int cols_pass(const DimTables<T>* tb, int part, long long inner, long lon
                         SegStride(), SegStride(), Outer2(), nullptr, 0, pro, epi);
   }
   const int N1 = tb->N1, N2 = tb->N2;
+  if (part == 3) {
+    // cluster kernel: tile = W columns x N rows per cluster of 8 CTAs; slices along blockIdx.y
+    ClusterParams<T> cp;
+    cp.es = inner; cp.os = inner * N; cp.ncols = inner; cp.scale = scale;
+    cp.tw1 = tb->tw1; cp.tw2 = tb->tw2; cp.twN = tb->twN;
+    if (pro) cp.pro = *pro; else cp.pro.on = 0;
+    if (epi) cp.epi = *epi; else cp.epi.on = 0;
+    const int Wc = cluster_cols(sizeof(T));
+    const long long ntiles = (inner + Wc - 1) / Wc;
+    FFB_REQUIRE(ntiles * 8 < (1ll << 31), FFB_EUNSUPPORTED, "too many tiles");
+    char pname[64];
+    snprintf(pname, sizeof(pname), "fft_cluster_%s_N%d", sizeof(T) == 8 ? "f64" : "f32", N);
+    ProfScope ps(pname, (double)inner * (double)outer * 2.0 * N * sizeof(cx<T>));
+    for (long long o0 = 0; o0 < outer; o0 += 65535) {
+      const long long cnt = std::min<long long>(65535, outer - o0);
+      cp.in = src + o0 * cp.os; cp.out = dst + o0 * cp.os;
+      if (pro && pro->w) cp.pro.w = pro->w + o0 * cp.os;
+      if (epi && epi->w) cp.epi.w = epi->w + o0 * cp.os;
+      if (epi && epi->acc) cp.epi.acc = epi->acc + o0 * cp.os;
+      FFB_REQUIRE(o0 == 0 || (!(pro && pro->ko) && !(epi && (epi->ko || epi->ao || epi->loo > 0))), FFB_EUNSUPPORTED, "fused pass with more than 65535 slices");
+      int rc = sizeof(T) == 8 ? cluster_launch_double(N, dir, &cp, ntiles, (int)cnt, st) : cluster_launch_float(N, dir, &cp, ntiles, (int)cnt, st);
+      if (rc == 1) return set_error(FFB_EUNSUPPORTED, "no cluster FFT kernel for N=%d", N);
+      if (rc) return rc;
+    }
+    return FFB_OK;
+  }
   Outer2 o2;
   o2.nhi = outer; o2.in_os2 = inner * N; o2.out_os2 = inner * N;
   if (part == 1) {  // length-N1 transforms over n1 (element stride N2*inner) for each n2, times exp(-/+2 pi i n2 k1/N)
@@ -386,7 +434,8 @@ static int exec_pow2(ffb_plan* pl, const void* in, void* out, int dir, const ffb
   std::vector<Op> ops;
   auto push_cols = [&](int d) {
     auto* tb = reinterpret_cast<DimTables<T>*>(pl->tables[d]);
-    if (tb->four) { ops.push_back({3, d, 1, false}); ops.push_back({3, d, 2, true}); }
+    if (tb->cluster) ops.push_back({3, d, 3, false});
+    else if (tb->four) { ops.push_back({3, d, 1, false}); ops.push_back({3, d, 2, true}); }
     else ops.push_back({3, d, 0, false});
   };
   if (pl->kind == FFB_C2C) { ops.push_back({0, 0, 0, false}); for (int d = 1; d < nd; ++d) push_cols(d); }

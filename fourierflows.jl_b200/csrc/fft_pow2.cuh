@@ -53,6 +53,7 @@ struct Pow2Params {
   };
   Fuse pro, epi;
   const T* rmul;                     // C2R_ROWS: real result multiplied by this real field (same layout as out)
+  int pf_ahead;                      // ROWS modes: prefetch the line this many tiles ahead into L2 (0 = off)
   const cx<T>* twN;                  // C2C_COLS_TW: exp(-2*pi*i*q/Nfull), q < Nfull
   int twN_mask;                      // Nfull - 1
   long long nlines;                  // lines per outer index
@@ -221,6 +222,20 @@ __global__ void __launch_bounds__(MAXT, MINB) fft_pow2_kernel(const Pow2Params<T
   const long long o_hi = blockIdx.y / (unsigned)p.outer_mod;
 
   cx<T> v[R];
+  // ---------------- L2 prefetch of the tile a later CTA on this SM will load (contiguous lines only) ----------------
+  // The row kernels are latency-bound at 2-4 CTAs/SM (ncu: long_scoreboard); pulling the line `pf_ahead` tiles ahead into
+  // L2 now turns its DRAM miss into an L2 hit when that CTA starts.
+  if constexpr (!COLS) {
+    if (p.pf_ahead > 0) {
+      const long long pl = line + (long long)p.pf_ahead * W;
+      if (pl < p.nlines) {
+        const char* base = reinterpret_cast<const char*>(reinterpret_cast<const cx<T>*>(p.in) + pl * p.in_ls);
+        constexpr int line_bytes = (MODE == C2R_ROWS ? (N + 1) : N) * (int)sizeof(cx<T>);
+#pragma unroll 1
+        for (int off = t * 128; off < line_bytes; off += Tn * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
+      }
+    }
+  }
   // ---------------- load ----------------
   if constexpr (MODE == C2R_ROWS) {
     // Z[k] = (X[k] + conj(X[N-k])) + i*exp(+i*pi*k/N)*(X[k] - conj(X[N-k]))
