@@ -238,6 +238,14 @@ static int choose_w(int N, int mode, long long nlines) {
 }
 
 // One register-resident pass over `nouter` outer blocks (gridDim.y chunks of <= 65535).
+// snake ordering state set by the pass scheduler (exec_pow2) for the next launch
+static thread_local int g_pass_reverse = 0, g_pass_keep = 0;
+static int snake_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("FFB_SNAKE"); v = e ? atoi(e) : 0; }
+  return v;
+}
+
 struct SegStride { int seg = 0; long long stride = 0; };  // seg = 0: unsegmented
 // two-level outer index (four-step sub-passes): blockIdx.y = o_lo + mod*o_hi -> o_lo*os + o_hi*os2
 struct Outer2 { int mod = 0; long long nhi = 1, in_os2 = 0, out_os2 = 0; };
@@ -252,6 +260,8 @@ static int pow2_pass(int N, int mode, int dir, const void* in, void* out, long l
   if (pro) p.pro = *pro; else p.pro.on = 0;
   if (epi) p.epi = *epi; else p.epi.on = 0;
   p.rmul = rmul;
+  p.reverse = g_pass_reverse;
+  p.keep_out = g_pass_keep;
   p.pf_ahead = 0;
   if (mode == C2C_ROWS || mode == R2C_ROWS || mode == C2R_ROWS) {
     // distance = one full wave of resident CTAs (tuning override: FFB_PF_AHEAD, 0 disables)
@@ -472,6 +482,8 @@ static int exec_pow2(ffb_plan* pl, const void* in, void* out, int dir, const ffb
     const void* s_ = buf(src[i]);
     void* d_ = buf(dst[i]);
     const T sc = (dir > 0 && i == n - 1) ? inv : T(1);
+    g_pass_reverse = snake_enabled() ? (i & 1) : 0;
+    g_pass_keep = (snake_enabled() && i + 1 < n) ? 1 : 0;
     int rc;
     if (op.kind == 0) rc = pow2_pass<T>(tb0->N, C2C_ROWS, dir, s_, d_, 1, tb0->N, 0, 1, tb0->N, 0, rows, 1, sc, tb0->tw, nullptr, st);
     else if (op.kind == 1) rc = pow2_pass<T>(tb0->N, R2C_ROWS, -1, s_, d_, 1, tb0->N, 0, 1, e[0], 0, rows, 1, T(1), tb0->tw, tb0->twr, st);
@@ -490,6 +502,7 @@ static int exec_pow2(ffb_plan* pl, const void* in, void* out, int dir, const ffb
       rc = cols_pass<T>(reinterpret_cast<DimTables<T>*>(pl->tables[op.d]), op.part, inner, outer, reinterpret_cast<const cx<T>*>(s_),
                         reinterpret_cast<cx<T>*>(d_), dir, sc, st, pro, epi);
     }
+    g_pass_reverse = 0; g_pass_keep = 0;
     if (rc) return rc;
   }
   return FFB_OK;

@@ -54,6 +54,9 @@ struct Pow2Params {
   Fuse pro, epi;
   const T* rmul;                     // C2R_ROWS: real result multiplied by this real field (same layout as out)
   int pf_ahead;                      // ROWS modes: prefetch the line this many tiles ahead into L2 (0 = off)
+  int reverse;                       // walk tiles / slices backwards (snake ordering between consecutive passes: the tail
+                                     // of what the previous kernel wrote is still in the 126 MB L2)
+  int keep_out;                      // 1: store with the default policy (data re-read by the next pass), 0: evict-first
   const cx<T>* twN;                  // C2C_COLS_TW: exp(-2*pi*i*q/Nfull), q < Nfull
   int twN_mask;                      // Nfull - 1
   long long nlines;                  // lines per outer index
@@ -190,6 +193,11 @@ template <typename T> FFB_D void stc(cx<T>* p, cx<T> c) {
   V q; q.x = c.x; q.y = c.y;
   __stcs(reinterpret_cast<V*>(p), q);
 }
+template <typename T> FFB_D void stk(cx<T>* p, cx<T> c, int keep) {
+  using V = typename vec2<T>::type;
+  V q; q.x = c.x; q.y = c.y;
+  if (keep) *reinterpret_cast<V*>(p) = q; else __stcs(reinterpret_cast<V*>(p), q);
+}
 
 // factor (cr + i ci) * k0[i0] * kt[it] * ko[io] * w[off], evaluated left to right like `im * kr * invKrsq * sol`
 template <typename T>
@@ -216,10 +224,12 @@ __global__ void __launch_bounds__(MAXT, MINB) fft_pow2_kernel(const Pow2Params<T
   const int tid = threadIdx.x;
   const int w = COLS ? tid % W : tid / Tn;
   const int t = COLS ? tid / W : tid % Tn;
-  const long long line = (long long)blockIdx.x * W + w;
+  const unsigned bx = p.reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
+  const unsigned by = p.reverse ? gridDim.y - 1 - blockIdx.y : blockIdx.y;
+  const long long line = (long long)bx * W + w;
   const bool active = line < p.nlines;
-  const int o_lo = (int)(blockIdx.y % (unsigned)p.outer_mod);
-  const long long o_hi = blockIdx.y / (unsigned)p.outer_mod;
+  const int o_lo = (int)(by % (unsigned)p.outer_mod);
+  const long long o_hi = by / (unsigned)p.outer_mod;
 
   cx<T> v[R];
   // ---------------- L2 prefetch of the tile a later CTA on this SM will load (contiguous lines only) ----------------
@@ -300,8 +310,8 @@ __global__ void __launch_bounds__(MAXT, MINB) fft_pow2_kernel(const Pow2Params<T
       const cx<T> s = v[m] + conj(zp), d = v[m] - conj(zp);
       const cx<T> x = half * (s + mul_mi(wk * d));
       if (active) {
-        stc(out + k, x);
-        if (k == 0) stc(out + N, mk<T>(v[m].x - v[m].y, T(0)));
+        stk(out + k, x, p.keep_out);
+        if (k == 0) stk(out + N, mk<T>(v[m].x - v[m].y, T(0)), p.keep_out);
       }
     });
   } else if constexpr (MODE == C2R_ROWS) {
@@ -355,10 +365,10 @@ __global__ void __launch_bounds__(MAXT, MINB) fft_pow2_kernel(const Pow2Params<T
         }
       } else if (sc != T(1)) {
 #pragma unroll
-        for (int m = 0; m < R; ++m) stc(out + off(t + m * Tn), sc * v[m]);
+        for (int m = 0; m < R; ++m) stk(out + off(t + m * Tn), sc * v[m], p.keep_out);
       } else {
 #pragma unroll
-        for (int m = 0; m < R; ++m) stc(out + off(t + m * Tn), v[m]);
+        for (int m = 0; m < R; ++m) stk(out + off(t + m * Tn), v[m], p.keep_out);
       }
     }
   }
