@@ -294,7 +294,10 @@ static int pow2_pass(int N, int mode, int dir, const void* in, void* out, long l
   // algorithmic bytes: every element of the line set is read once and written once
   const double lines = (double)nlines * (double)nouter * (double)(o2.mod ? o2.nhi : 1);
   const double in_elems = (mode == C2R_ROWS) ? N + 1 : N, out_elems = (mode == R2C_ROWS) ? N + 1 : N;
-  ProfScope ps(pname, lines * (in_elems + out_elems) * sizeof(cx<T>));
+  // fused operands are algorithmic traffic too: dense factor (one real per element), accumulated array, physical multiplier
+  const double fused_bytes = lines * N * ((pro && pro->w ? sizeof(T) : 0) + (epi && epi->w ? sizeof(T) : 0) + (epi && epi->acc ? sizeof(cx<T>) : 0) +
+                                          (rmul ? sizeof(cx<T>) : 0));
+  ProfScope ps(pname, lines * (in_elems + out_elems) * sizeof(cx<T>) + fused_bytes);
   if (o2.mod) {
     // nouter = o2.mod low indices per high index; chunk over the high index so that gridDim.y <= 65535
     FFB_REQUIRE(o2.mod <= 65535, FFB_EUNSUPPORTED, "four-step factor too large");

@@ -143,12 +143,14 @@ template <typename T, int R, int r, int b> FFB_D void apply_twiddle_powers(cx<T>
 template <typename T, int DIR, bool COLS, int R, int N, int Ns, int TWOFF, int r, int... Rest>
 FFB_D void run_passes(cx<T> (&v)[R], int t, int w, int W, typename xword<T>::type* xb, const cx<T>* tw) {
   constexpr int Tn = N / R, nb = R / r;
+  cx<T> wb[nb];
+  if constexpr (Ns > 1) {
+#pragma unroll
+    for (int b = 0; b < nb; ++b) wb[b] = load_tw<T, DIR>(tw + TWOFF + ((t + b * Tn) & (Ns - 1)));
+  }
   static_for<0, nb>([&](auto B) {
     constexpr int b = decltype(B)::value;
-    if constexpr (Ns > 1) {
-      const int a = (t + b * Tn) & (Ns - 1);
-      apply_twiddle_powers<T, R, r, b>(v, load_tw<T, DIR>(tw + TWOFF + a));
-    }
+    if constexpr (Ns > 1) apply_twiddle_powers<T, R, r, b>(v, wb[b]);
     bfly_at<DIR, R, r, b>(v);
   });
   if constexpr (sizeof...(Rest) > 0) {
@@ -199,6 +201,8 @@ template <typename T> FFB_D void stk(cx<T>* p, cx<T> c, int keep) {
   if (keep) *reinterpret_cast<V*>(p) = q; else __stcs(reinterpret_cast<V*>(p), q);
 }
 
+FFB_D void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // factor (cr + i ci) * k0[i0] * kt[it] * ko[io] * w[off], evaluated left to right like `im * kr * invKrsq * sol`
 template <typename T>
 FFB_D cx<T> fuse_factor(T cr, T ci, const T* k0, const T* kt, const T* ko, const T* w, int i0, int it, long long io, long long off) {
@@ -231,6 +235,35 @@ __global__ void __launch_bounds__(MAXT, MINB) fft_pow2_kernel(const Pow2Params<T
   const int o_lo = (int)(by % (unsigned)p.outer_mod);
   const long long o_hi = by / (unsigned)p.outer_mod;
 
+  // ---------------- fused operands: pull them towards L2 now, they are consumed only after the data has arrived ----------------
+  // (ncu: without this the dense factor / accumulated array / multiplier field cost a second exposed DRAM round trip per CTA)
+  if (active) {
+    if constexpr (MODE == C2C_COLS || MODE == C2C_COLS_TW) {
+      if (p.pro.on && p.pro.w) {
+        const T* wp = p.pro.w + o_lo * p.in_os + o_hi * p.in_os2 + line * p.in_ls;
+#pragma unroll
+        for (int m = 0; m < R; ++m) {
+          const int i = t + m * Tn;
+          prefetch_l2(wp + (long long)(i & p.in_seg_mask) * p.in_es + (long long)(i >> p.in_seg_shift) * p.in_seg_stride);
+        }
+      }
+      if (p.epi.on && p.epi.acc) {
+        const cx<T>* ap = p.epi.acc + o_lo * p.out_os + o_hi * p.out_os2 + line * p.out_ls;
+#pragma unroll
+        for (int m = 0; m < R; ++m) {
+          const int i = t + m * Tn;
+          prefetch_l2(ap + (long long)(i & p.out_seg_mask) * p.out_es + (long long)(i >> p.out_seg_shift) * p.out_seg_stride);
+        }
+      }
+    }
+    if constexpr (MODE == C2R_ROWS) {
+      if (p.rmul) {
+        const char* mp = reinterpret_cast<const char*>(reinterpret_cast<const cx<T>*>(p.rmul) + o_lo * p.out_os + o_hi * p.out_os2 + line * p.out_ls);
+#pragma unroll 1
+        for (int off = t * 128; off < N * (int)sizeof(cx<T>); off += Tn * 128) prefetch_l2(mp + off);
+      }
+    }
+  }
   cx<T> v[R];
   // ---------------- L2 prefetch of the tile a later CTA on this SM will load (contiguous lines only) ----------------
   // The row kernels are latency-bound at 2-4 CTAs/SM (ncu: long_scoreboard); pulling the line `pf_ahead` tiles ahead into
@@ -251,15 +284,24 @@ __global__ void __launch_bounds__(MAXT, MINB) fft_pow2_kernel(const Pow2Params<T
     // Z[k] = (X[k] + conj(X[N-k])) + i*exp(+i*pi*k/N)*(X[k] - conj(X[N-k]))
     const cx<T>* in = reinterpret_cast<const cx<T>*>(p.in) + o_lo * p.in_os + o_hi * p.in_os2 + line * p.in_ls;
     const cx<T> wbase = load_tw<T, -1>(p.twr + t);
-    static_for<0, R>([&](auto M) {
-      constexpr int m = decltype(M)::value;
-      const int k = t + m * Tn;
-      cx<T> a = mk<T>(0, 0), b = mk<T>(0, 0);
-      if (active) { a = ldc(in + k); b = ldc(in + (N - k)); }
-      if (k == 0) { a.y = T(0); b.y = T(0); }  // c2r ignores Im X[0] and Im X[N] (FFTW / cuFFT / pocketfft convention)
-      const cx<T> wk = conj(split_twiddle<T, R, N, m>(p.twr, wbase, t));
-      const cx<T> s = a + conj(b), d = a - conj(b);
-      v[m] = s + mul_i(wk * d);
+    // all loads of X[k] first, then the partners X[N-k] in batches: independent loads are in flight together
+#pragma unroll
+    for (int m = 0; m < R; ++m) v[m] = active ? ldc(in + (t + m * Tn)) : mk<T>(0, 0);
+    constexpr int CB = R < 8 ? R : 8;
+    static_for<0, R / CB>([&](auto MB) {
+      constexpr int m0 = decltype(MB)::value * CB;
+      cx<T> bv[CB];
+#pragma unroll
+      for (int q = 0; q < CB; ++q) bv[q] = active ? ldc(in + (N - (t + (m0 + q) * Tn))) : mk<T>(0, 0);
+      static_for<0, CB>([&](auto Q) {
+        constexpr int m = m0 + decltype(Q)::value;
+        const int k = t + m * Tn;
+        cx<T> a = v[m], b = bv[m - m0];
+        if (k == 0) { a.y = T(0); b.y = T(0); }  // c2r ignores Im X[0] and Im X[N] (FFTW / cuFFT / pocketfft convention)
+        const cx<T> wk = conj(split_twiddle<T, R, N, m>(p.twr, wbase, t));
+        const cx<T> s = a + conj(b), d = a - conj(b);
+        v[m] = s + mul_i(wk * d);
+      });
     });
   } else {
     const cx<T>* in = reinterpret_cast<const cx<T>*>(p.in) + o_lo * p.in_os + o_hi * p.in_os2 + line * p.in_ls;
@@ -272,11 +314,24 @@ __global__ void __launch_bounds__(MAXT, MINB) fft_pow2_kernel(const Pow2Params<T
       const int i0 = (int)(line % p.pro.n0);
       const long long io = p.pro.other_from_col == 1 ? line / p.pro.n0 : (p.pro.other_from_col == 2 ? (long long)o_lo : o_hi);
       const long long base = (in - reinterpret_cast<const cx<T>*>(p.in));
+      // the dense factor is loaded in batches (independent loads first, uses after) so its latency is paid once per batch
+      constexpr int PB = R < 8 ? R : 8;
 #pragma unroll
-      for (int m = 0; m < R; ++m) {
-        const int i = t + m * Tn;
-        const long long off = base + (long long)(i & p.in_seg_mask) * p.in_es + (long long)(i >> p.in_seg_shift) * p.in_seg_stride;
-        v[m] = fuse_factor<T>(p.pro.cr, p.pro.ci, p.pro.k0, p.pro.kt, p.pro.ko, p.pro.w, i0, p.pro.idm * i + p.pro.ido * o_lo, io, off) * v[m];
+      for (int m0 = 0; m0 < R; m0 += PB) {
+        T wv[PB];
+#pragma unroll
+        for (int q = 0; q < PB; ++q) {
+          const int i = t + (m0 + q) * Tn;
+          const long long off = base + (long long)(i & p.in_seg_mask) * p.in_es + (long long)(i >> p.in_seg_shift) * p.in_seg_stride;
+          wv[q] = p.pro.w ? __ldcs(p.pro.w + off) : T(1);
+        }
+#pragma unroll
+        for (int q = 0; q < PB; ++q) {
+          const int i = t + (m0 + q) * Tn;
+          cx<T> f = fuse_factor<T>(p.pro.cr, p.pro.ci, p.pro.k0, p.pro.kt, p.pro.ko, (const T*)nullptr, i0, p.pro.idm * i + p.pro.ido * o_lo, io, 0);
+          if (p.pro.w) f = mk<T>(f.x * wv[q], f.y * wv[q]);
+          v[m0 + q] = f * v[m0 + q];
+        }
       }
     }
   }
@@ -320,10 +375,14 @@ __global__ void __launch_bounds__(MAXT, MINB) fft_pow2_kernel(const Pow2Params<T
       const T sc = p.scale;
       if (p.rmul) {
         const cx<T>* mulp = reinterpret_cast<const cx<T>*>(p.rmul) + o_lo * p.out_os + o_hi * p.out_os2 + line * p.out_ls;
+        constexpr int MB = R < 4 ? R : 4;
 #pragma unroll
-        for (int m = 0; m < R; ++m) {
-          const cx<T> z = ldc(mulp + (t + m * Tn));   // two consecutive reals of the multiplier field
-          stc(out + (t + m * Tn), mk<T>(sc * v[m].x * z.x, sc * v[m].y * z.y));
+        for (int m0 = 0; m0 < R; m0 += MB) {
+          cx<T> z[MB];
+#pragma unroll
+          for (int q = 0; q < MB; ++q) z[q] = ldc(mulp + (t + (m0 + q) * Tn));   // two consecutive reals of the multiplier field
+#pragma unroll
+          for (int q = 0; q < MB; ++q) stc(out + (t + (m0 + q) * Tn), mk<T>(sc * v[m0 + q].x * z[q].x, sc * v[m0 + q].y * z[q].y));
         }
       } else {
 #pragma unroll
@@ -333,12 +392,15 @@ __global__ void __launch_bounds__(MAXT, MINB) fft_pow2_kernel(const Pow2Params<T
   } else {
     if constexpr (MODE == C2C_COLS_TW) {
       // inter-pass twiddle of the four-step split: k1 = t + m*Tn, n2 = o_lo (same value for every column of the tile)
+      constexpr int TB = R < 4 ? R : 4;
 #pragma unroll
-      for (int m = 1; m < R; ++m) {
-        const int q = (o_lo * (t + m * Tn)) & p.twN_mask;
-        v[m] = v[m] * load_tw<T, DIR>(p.twN + q);
+      for (int m0 = 0; m0 < R; m0 += TB) {
+        cx<T> wv[TB];
+#pragma unroll
+        for (int q = 0; q < TB; ++q) wv[q] = load_tw<T, DIR>(p.twN + ((o_lo * (t + (m0 + q) * Tn)) & p.twN_mask));
+#pragma unroll
+        for (int q = 0; q < TB; ++q) v[m0 + q] = v[m0 + q] * wv[q];
       }
-      if (t != 0) v[0] = v[0] * load_tw<T, DIR>(p.twN + ((o_lo * t) & p.twN_mask));
     }
     if (active) {
       cx<T>* out = reinterpret_cast<cx<T>*>(p.out) + o_lo * p.out_os + o_hi * p.out_os2 + line * p.out_ls;
@@ -349,19 +411,30 @@ __global__ void __launch_bounds__(MAXT, MINB) fft_pow2_kernel(const Pow2Params<T
         const long long io = p.epi.other_from_col == 1 ? line / p.epi.n0 : (p.epi.other_from_col == 2 ? (long long)o_lo : o_hi);
         const long long base = (out - reinterpret_cast<cx<T>*>(p.out));
         const bool dead0 = p.epi.dealias && ((p.epi.lo0 > 0 && i0 >= p.epi.lo0 - 1 && i0 < p.epi.hi0) || (p.epi.loo > 0 && io >= p.epi.loo - 1 && io < p.epi.hio));
+        constexpr int EB = R < 4 ? R : 4;
 #pragma unroll
-        for (int m = 0; m < R; ++m) {
-          const int i = t + m * Tn;
-          const int it = p.epi.idm * i + p.epi.ido * o_lo;
-          const long long o = off(i);
-          cx<T> r;
-          if (dead0 || (p.epi.dealias && p.epi.lot > 0 && it >= p.epi.lot - 1 && it < p.epi.hit)) {
-            r = mk<T>(0, 0);
-          } else {
-            r = fuse_factor<T>(p.epi.cr, p.epi.ci, p.epi.k0, p.epi.kt, p.epi.ko, p.epi.w, i0, it, io, base + o) * (sc * v[m]);
-            if (p.epi.acc) r = r + fuse_factor<T>(p.epi.ar, p.epi.ai, p.epi.a0, p.epi.at, p.epi.ao, (const T*)nullptr, i0, it, io, 0) * ldc(p.epi.acc + base + o);
+        for (int m0 = 0; m0 < R; m0 += EB) {
+          cx<T> av[EB];
+          bool dead[EB];
+#pragma unroll
+          for (int q = 0; q < EB; ++q) {   // independent loads of the accumulated array first
+            const int i = t + (m0 + q) * Tn;
+            const int it = p.epi.idm * i + p.epi.ido * o_lo;
+            dead[q] = dead0 || (p.epi.dealias && p.epi.lot > 0 && it >= p.epi.lot - 1 && it < p.epi.hit);
+            av[q] = (p.epi.acc && !dead[q]) ? ldc(p.epi.acc + base + off(i)) : mk<T>(0, 0);
           }
-          stc(out + o, r);
+#pragma unroll
+          for (int q = 0; q < EB; ++q) {
+            const int i = t + (m0 + q) * Tn;
+            const int it = p.epi.idm * i + p.epi.ido * o_lo;
+            const long long o = off(i);
+            cx<T> r = mk<T>(0, 0);
+            if (!dead[q]) {
+              r = fuse_factor<T>(p.epi.cr, p.epi.ci, p.epi.k0, p.epi.kt, p.epi.ko, p.epi.w, i0, it, io, base + o) * (sc * v[m0 + q]);
+              if (p.epi.acc) r = r + fuse_factor<T>(p.epi.ar, p.epi.ai, p.epi.a0, p.epi.at, p.epi.ao, (const T*)nullptr, i0, it, io, 0) * av[q];
+            }
+            stc(out + o, r);
+          }
         }
       } else if (sc != T(1)) {
 #pragma unroll

@@ -2,6 +2,7 @@
 // precompute of src/timesteppers.jl:673-721, the closed elementwise vocabulary used by calcN! implementations
 // (src/diffusion.jl:136-140) and the Parseval reductions of src/utils.jl:113-183.
 #include <complex>
+#include <type_traits>
 #include "ffb_common.cuh"
 
 namespace ffb {
@@ -204,8 +205,20 @@ __global__ void axpby_kernel(void* out, T a, const void* x, T b, const void* y, 
 
 template <typename T>
 __global__ void mul_real_kernel(T* out, const T* x, const T* y, long long n) {
+  // 16-byte vectors when all three arrays are 16-byte aligned, scalar tail / fallback otherwise
+  constexpr int V = 16 / sizeof(T);
+  using V4 = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = x[i] * y[i];
+  const bool aligned = ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+  const long long nv = aligned ? n / V : 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+    const V4 a = reinterpret_cast<const V4*>(x)[i], b = reinterpret_cast<const V4*>(y)[i];
+    V4 r;
+    if constexpr (sizeof(T) == 4) { r.x = a.x * b.x; r.y = a.y * b.y; r.z = a.z * b.z; r.w = a.w * b.w; }
+    else { r.x = a.x * b.x; r.y = a.y * b.y; }
+    reinterpret_cast<V4*>(out)[i] = r;
+  }
+  for (long long i = nv * V + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = x[i] * y[i];
 }
 
 template <typename T> FFB_D T ipow(T v, int p) {  // p >= 1; `k^2` is `k*k` in Julia (literal_pow)
