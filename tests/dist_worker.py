@@ -51,7 +51,12 @@ def main():
         for s in range(3):
             cp.stepforward(1)
             fo.stepforward(ob, 1)
-            e = relerr(cp.sol.to_numpy(), ff.spectral_slab(ob.sol, P, rank))
+            # relative L2 error of the GLOBAL state: slabs that hold only high wavenumbers are ~1e-20 and have no meaningful
+            # relative error of their own
+            ref = ff.spectral_slab(ob.sol, P, rank)
+            acc = torch.tensor([float(np.sum(np.abs(cp.sol.to_numpy() - ref) ** 2)), float(np.sum(np.abs(ref) ** 2))], device="cuda", dtype=torch.float64)
+            dist.all_reduce(acc)
+            e = float(torch.sqrt(acc[0] / acc[1]).item())
             worst = max(worst, e / ((s + 1) * tol))
         if rank == 0:
             print(f"dist burgers {stepper} {np.dtype(T).name}: rel-L2 after 3 steps {e:.2e}", flush=True)
