@@ -96,6 +96,12 @@ SIGNATURES = {
     "ffb_dist_info": [_vp, _P(_i), _P(_i)],
     "ffb_dist_alltoall": [_vp, _vp, _vp, _sz],
     "ffb_plan_create_dist": [_P(_vp), _i, _P(_i64), _i, _vp, _i],
+    "ffb_plan_dist_recv_buffers": [_vp, _P(_vp), _P(_vp), _P(_sz)],
+    "ffb_plan_dist_set_peers": [_vp, _P(_vp), _P(_vp)],
+    "ffb_dist_ipc_export": [_vp, _vp],
+    "ffb_dist_ipc_open": [_vp, _P(_vp)],
+    "ffb_dist_ipc_close": [_vp],
+    "ffb_dist_barrier": [_vp],
     "ffb_wavenumbers": [_vp, _i64, _d, _i, _i],
     "ffb_ksq": [_vp, _vp, _vp, _vp, _vp, _P(ffb_desc)],
     "ffb_dealias": [_vp, _P(ffb_desc)],
@@ -116,6 +122,7 @@ SIGNATURES = {
     "ffb_problem_create": [_P(_vp), _P(ffb_problem_config)],
     "ffb_problem_destroy": [_vp],
     "ffb_problem_sol": [_vp, _P(_vp), _P(_i64)],
+    "ffb_problem_plan": [_vp, _P(_vp)],
     "ffb_problem_clock": [_vp, _P(_d), _P(_i64), _P(_d)],
     "ffb_problem_set_dt": [_vp, _d],
     "ffb_problem_bytes": [_vp, _P(_sz)],

@@ -68,6 +68,14 @@ class CProblem:
         L.call("ffb_problem_clock", self._h, C.byref(t), C.byref(step), C.byref(dt))
         return t.value, step.value, dt.value
 
+    def enable_p2p(self):
+        """slab-decomposed problems: fused pass + collective exchange (collective call on every rank)"""
+        from .dist import enable_p2p
+        ph = C.c_void_p()
+        L.call("ffb_problem_plan", self._h, C.byref(ph))
+        enable_p2p(ph, self.dist)
+        return self
+
     def device_bytes(self):
         b = C.c_size_t()
         L.call("ffb_problem_bytes", self._h, C.byref(b))

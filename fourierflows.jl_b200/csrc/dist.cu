@@ -17,6 +17,7 @@ struct NcclApi {
   int (*GroupEnd)() = nullptr;
   int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
   int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
   int (*GetVersion)(int*) = nullptr;
 };
@@ -39,6 +40,7 @@ static int load_nccl() {
   g_nccl.GroupEnd = (int (*)())dlsym(h, "ncclGroupEnd");
   g_nccl.Send = (int (*)(const void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclSend");
   g_nccl.Recv = (int (*)(void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclRecv");
+  g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclAllReduce");
   g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
   g_nccl.GetVersion = (int (*)(int*))dlsym(h, "ncclGetVersion");
   if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.Send || !g_nccl.Recv || !g_nccl.GroupStart || !g_nccl.GroupEnd)
@@ -57,6 +59,13 @@ cudaEvent_t dist_next_event(ffb_dist* d) {
   cudaEvent_t e = d->ev[d->ev_next];
   d->ev_next = (d->ev_next + 1) % 64;
   return e;
+}
+
+int dist_barrier(ffb_dist* d, cudaStream_t st) {
+  if (d->nranks == 1) return FFB_OK;
+  FFB_REQUIRE(g_nccl.AllReduce, FFB_ENCCL, "ncclAllReduce not available");
+  FFB_NCCL(g_nccl.AllReduce(d->barrier_buf, d->barrier_buf, 1, /*ncclFloat32*/ 7, /*ncclSum*/ 0, d->comm, st));
+  return FFB_OK;
 }
 
 int dist_alltoall_bytes(ffb_dist* d, const void* sendbuf, void* recvbuf, size_t count, size_t stride, cudaStream_t st) {
@@ -100,6 +109,8 @@ int ffb_dist_init(ffb_dist** out, int rank, int nranks, const void* id128) {
   if (r != 0) { delete d; return set_error(FFB_ENCCL, "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); }
   FFB_CUDA(cudaStreamCreateWithFlags(&d->comm_stream, cudaStreamNonBlocking));
   for (auto& e : d->ev) FFB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  FFB_CUDA(cudaMalloc(&d->barrier_buf, 256));
+  FFB_CUDA(cudaMemset(d->barrier_buf, 0, 256));
   *out = d;
   return FFB_OK;
 }
@@ -110,6 +121,7 @@ int ffb_dist_destroy(ffb_dist* d) {
   if (d->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(d->comm);
   for (auto& e : d->ev) cudaEventDestroy(e);
   cudaStreamDestroy(d->comm_stream);
+  cudaFree(d->barrier_buf);
   delete d;
   return FFB_OK;
 }
@@ -119,6 +131,35 @@ int ffb_dist_info(const ffb_dist* d, int* rank, int* nranks) {
   if (rank) *rank = d->rank;
   if (nranks) *nranks = d->nranks;
   return FFB_OK;
+}
+
+// CUDA IPC plumbing for the fused pass + collective path: a rank exports the handle of one of its buffers (64 bytes), the
+// launcher moves it to the other ranks, which map it (peer access is enabled lazily).
+int ffb_dist_ipc_export(void* dev_ptr, void* host_handle64) {
+  FFB_REQUIRE(dev_ptr && host_handle64, FFB_EINVAL, "NULL argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "unexpected IPC handle size");
+  cudaIpcMemHandle_t h;
+  FFB_CUDA(cudaIpcGetMemHandle(&h, dev_ptr));
+  memcpy(host_handle64, &h, 64);
+  return FFB_OK;
+}
+
+int ffb_dist_ipc_open(const void* host_handle64, void** dev_ptr) {
+  FFB_REQUIRE(dev_ptr && host_handle64, FFB_EINVAL, "NULL argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, host_handle64, 64);
+  FFB_CUDA(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return FFB_OK;
+}
+
+int ffb_dist_ipc_close(void* dev_ptr) {
+  if (dev_ptr) FFB_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+  return FFB_OK;
+}
+
+int ffb_dist_barrier(ffb_dist* d) {
+  FFB_REQUIRE(d, FFB_EINVAL, "dist is NULL");
+  return dist_barrier(d, current_stream());
 }
 
 // test / bench aid: all-to-all of equal blocks (block_bytes per peer) on the library stream

@@ -10,6 +10,7 @@ struct ffb_dist {
   cudaStream_t comm_stream;
   cudaEvent_t ev[64];      // ring of events for compute <-> comm ordering
   int ev_next;
+  float* barrier_buf;      // device scratch of the barrier all-reduce
 };
 
 namespace ffb {
@@ -17,4 +18,7 @@ namespace ffb {
 // (the own block is a device-to-device copy).  Enqueued on `st`.
 int dist_alltoall_bytes(ffb_dist* d, const void* sendbuf, void* recvbuf, size_t count, size_t stride_bytes, cudaStream_t st);
 cudaEvent_t dist_next_event(ffb_dist* d);
+// stream-ordered barrier across all ranks (1-element NCCL all-reduce): every rank's earlier work on `st` has completed
+// (including its stores into peer memory) before any rank's later work starts
+int dist_barrier(ffb_dist* d, cudaStream_t st);
 }  // namespace ffb

@@ -84,6 +84,11 @@ struct ffb_plan {
   ffb_dist* dist;     // non-NULL: slab-decomposed 3-D r2c plan (physical z-slabs <-> spectral y-slabs)
   long long nyl, nzl; // local extents: spectral (nkr, nyl, nz), physical (nx, ny, nzl)
   int nchunks;        // exchange chunks along the local z range (overlap of all-to-all and local passes)
+  // fused pass + collective: double-buffered receive buffers and their peer mappings (CUDA IPC)
+  void* recv[2];
+  void* peers[2][8];
+  bool p2p;
+  int p2p_cur;
 };
 
 namespace ffb {
@@ -255,8 +260,16 @@ static int pow2_pass(int N, int mode, int dir, const void* in, void* out, long l
                      long long out_es, long long out_ls, long long out_os, long long nlines, long long nouter, T scale,
                      const cx<T>* tw, const cx<T>* twr, cudaStream_t st, SegStride in_seg = SegStride(), SegStride out_seg = SegStride(),
                      Outer2 o2 = Outer2(), const cx<T>* twN = nullptr, int twN_mask = 0,
-                     const typename Pow2Params<T>::Fuse* pro = nullptr, const typename Pow2Params<T>::Fuse* epi = nullptr, const T* rmul = nullptr) {
+                     const typename Pow2Params<T>::Fuse* pro = nullptr, const typename Pow2Params<T>::Fuse* epi = nullptr, const T* rmul = nullptr,
+                     cx<T>* const* peer_out = nullptr, int npeers = 0) {
   Pow2Params<T> p;
+  p.use_peer = 0;
+  for (int q = 0; q < 8; ++q) p.out_peer[q] = nullptr;
+  if (peer_out) {
+    FFB_REQUIRE(npeers <= 8 && nouter <= 65535 && !o2.mod, FFB_EUNSUPPORTED, "peer-store pass: at most 8 ranks and 65535 slices");
+    p.use_peer = 1;
+    for (int q = 0; q < npeers; ++q) p.out_peer[q] = peer_out[q];
+  }
   if (pro) p.pro = *pro; else p.pro.on = 0;
   if (epi) p.epi = *epi; else p.epi.on = 0;
   p.rmul = rmul;
@@ -632,6 +645,30 @@ static int exec_dist(ffb_plan* pl, const void* in, void* out, int dir) {
   long double tot = (long double)pl->n[0] * ny * nz;
   const T inv = (T)(1.0L / tot);
   SegStride seg; seg.seg = (int)nyl; seg.stride = blk;
+  if (pl->p2p) {
+    // ---- fused pass + collective: the pass before the exchange stores directly into the peers' receive buffers (NVLink),
+    //      one stream-ordered barrier replaces the all-to-all; receive buffers are double-buffered across transforms ----
+    const int cur = pl->p2p_cur;
+    pl->p2p_cur ^= 1;
+    cx<T>* mine = reinterpret_cast<cx<T>*>(pl->recv[cur]);
+    cx<T>* dests[8];
+    for (int q = 0; q < P; ++q) dests[q] = reinterpret_cast<cx<T>*>(pl->peers[cur][q]) + (long long)d->rank * blk;
+    if (dir < 0) {
+      if ((rc = pow2_pass<T>(N0, R2C_ROWS, -1, in, w0, 1, N0, 0, 1, nkr, 0, ny * nzl, 1, T(1), tb0->tw, tb0->twr, st))) return rc;
+      { ProfScope ps("fft_y_pass_peer_store", 0);
+      if ((rc = pow2_pass<T>((int)ny, C2C_COLS, -1, w0, mine, nkr, 1, nkr * ny, nkr, 1, nkr * nyl, nkr, nzl, T(1), tb1->tw, nullptr, st, SegStride(), seg,
+                             Outer2(), nullptr, 0, nullptr, nullptr, nullptr, dests, P))) return rc; }
+      if ((rc = dist_barrier(d, st))) return rc;
+      return pow2_pass<T>((int)nz, C2C_COLS, -1, mine, out, nkr * nyl, 1, 0, nkr * nyl, 1, 0, nkr * nyl, 1, T(1), tb2->tw, nullptr, st);
+    }
+    SegStride segz; segz.seg = (int)nzl; segz.stride = blk;
+    { ProfScope ps("fft_z_pass_peer_store", 0);
+    if ((rc = pow2_pass<T>((int)nz, C2C_COLS, +1, in, mine, nkr * nyl, 1, 0, nkr * nyl, 1, 0, nkr * nyl, 1, T(1), tb2->tw, nullptr, st, SegStride(), segz,
+                           Outer2(), nullptr, 0, nullptr, nullptr, nullptr, dests, P))) return rc; }
+    if ((rc = dist_barrier(d, st))) return rc;
+    if ((rc = pow2_pass<T>((int)ny, C2C_COLS, +1, mine, w2, nkr, 1, nkr * nyl, nkr, 1, nkr * ny, nkr, nzl, T(1), tb1->tw, nullptr, st, seg, SegStride()))) return rc;
+    return pow2_pass<T>(N0, C2R_ROWS, +1, w2, out, 1, nkr, 0, 1, N0, 0, ny * nzl, 1, inv, tb0->tw, tb0->twr, st);
+  }
   if (dir < 0) {
     cx<T>* spec = reinterpret_cast<cx<T>*>(out);
     // x: real (nx, ny, nzl) -> w0 (nkr, ny, nzl)
@@ -697,6 +734,8 @@ int ffb_plan_create(ffb_plan** out, int ndim, const int64_t* n, int dtype, int k
   auto* pl = new ffb_plan();
   pl->ndim = ndim; pl->dtype = dtype; pl->kind = kind; pl->nbatch = nbatch; pl->flags = flags;
   pl->dist = nullptr; pl->nyl = pl->nzl = 0; pl->nchunks = 1;
+  pl->recv[0] = pl->recv[1] = nullptr; pl->p2p = false; pl->p2p_cur = 0;
+  for (int b = 0; b < 2; ++b) for (int q = 0; q < 8; ++q) pl->peers[b][q] = nullptr;
   for (int d = 0; d < 3; ++d) { pl->n[d] = d < ndim ? n[d] : 1; pl->nc[d] = pl->n[d]; pl->tables[d] = nullptr; pl->ws[d] = nullptr; }
   if (kind == FFB_R2C) pl->nc[0] = pl->n[0] / 2 + 1;
   pl->ws_bytes = (size_t)pl->nc[0] * pl->nc[1] * pl->nc[2] * nbatch * 2 * dtype_size(dtype);
@@ -731,10 +770,37 @@ int ffb_plan_create_dist(ffb_plan** out, int ndim, const int64_t* n, int dtype, 
   return FFB_OK;
 }
 
+int ffb_plan_dist_recv_buffers(ffb_plan* pl, void** buf0, void** buf1, size_t* bytes_each) {
+  FFB_REQUIRE(pl && pl->dist && buf0 && buf1, FFB_EINVAL, "needs a slab-decomposed plan");
+  for (int b = 0; b < 2; ++b)
+    if (!pl->recv[b]) { int rc = ffb_malloc(&pl->recv[b], pl->ws_bytes); if (rc) return rc; }
+  *buf0 = pl->recv[0]; *buf1 = pl->recv[1];
+  if (bytes_each) *bytes_each = pl->ws_bytes;
+  return FFB_OK;
+}
+
+int ffb_plan_dist_set_peers(ffb_plan* pl, void* const* peers0, void* const* peers1) {
+  FFB_REQUIRE(pl && pl->dist && peers0 && peers1, FFB_EINVAL, "needs a slab-decomposed plan");
+  FFB_REQUIRE(pl->recv[0] && pl->recv[1], FFB_EINVAL, "call ffb_plan_dist_recv_buffers first");
+  const int P = pl->dist->nranks;
+  FFB_REQUIRE(P <= 8, FFB_EUNSUPPORTED, "peer-store exchange supports up to 8 ranks (one NVSwitch domain)");
+  FFB_REQUIRE(is_pow2((uint64_t)pl->nzl), FFB_EUNSUPPORTED, "nz / nranks must be a power of two");
+  for (int q = 0; q < P; ++q) {
+    FFB_REQUIRE(peers0[q] && peers1[q], FFB_EINVAL, "peer pointer %d is NULL", q);
+    pl->peers[0][q] = peers0[q]; pl->peers[1][q] = peers1[q];
+  }
+  FFB_REQUIRE(pl->peers[0][pl->dist->rank] == pl->recv[0] && pl->peers[1][pl->dist->rank] == pl->recv[1], FFB_EINVAL,
+              "the entry of the own rank must be the local receive buffer");
+  pl->p2p = true;
+  pl->desc += "peer-store-exchange ";
+  return FFB_OK;
+}
+
 int ffb_plan_destroy(ffb_plan* pl) {
   if (!pl) return FFB_OK;
   if (pl->dtype == FFB_F64) free_tables<double>(pl); else free_tables<float>(pl);
   for (int i = 0; i < 3; ++i) cudaFree(pl->ws[i]);
+  cudaFree(pl->recv[0]); cudaFree(pl->recv[1]);
   delete pl;
   return FFB_OK;
 }

@@ -35,6 +35,10 @@ struct Pow2Params {
   // so a pass can read / write destination-rank-major blocks without a pack kernel.  Unsegmented: mask = ~0, shift = 31.
   int in_seg_mask, in_seg_shift, out_seg_mask, out_seg_shift;
   long long in_seg_stride, out_seg_stride;
+  // Fused pass + collective (slab decomposition): when use_peer != 0 output segment s = (i >> out_seg_shift) is stored
+  // straight into rank s's receive buffer (peer memory mapped through CUDA IPC, NVLink stores) instead of out + s*seg_stride.
+  cx<T>* out_peer[8];
+  int use_peer;
   // two-level outer index: blockIdx.y = o -> (o % outer_mod)*os + (o / outer_mod)*os2   (outer_mod = 1<<30 when unused)
   int outer_mod;
   long long in_os2, out_os2;
@@ -406,7 +410,17 @@ __global__ void __launch_bounds__(MAXT, MINB) fft_pow2_kernel(const Pow2Params<T
       cx<T>* out = reinterpret_cast<cx<T>*>(p.out) + o_lo * p.out_os + o_hi * p.out_os2 + line * p.out_ls;
       const T sc = p.scale;
       auto off = [&](int i) { return (long long)(i & p.out_seg_mask) * p.out_es + (long long)(i >> p.out_seg_shift) * p.out_seg_stride; };
-      if (p.epi.on) {
+      if (p.use_peer) {
+        const long long lo = o_lo * p.out_os + o_hi * p.out_os2 + line * p.out_ls;
+#pragma unroll
+        for (int m = 0; m < R; ++m) {
+          const int i = t + m * Tn;
+          cx<T>* dstp = p.out_peer[i >> p.out_seg_shift] + lo + (long long)(i & p.out_seg_mask) * p.out_es;
+          using V = typename vec2<T>::type;
+          V q; q.x = sc * v[m].x; q.y = sc * v[m].y;
+          *reinterpret_cast<V*>(dstp) = q;   // NVLink store (or local for the own segment)
+        }
+      } else if (p.epi.on) {
         const int i0 = (int)(line % p.epi.n0);
         const long long io = p.epi.other_from_col == 1 ? line / p.epi.n0 : (p.epi.other_from_col == 2 ? (long long)o_lo : o_hi);
         const long long base = (out - reinterpret_cast<cx<T>*>(p.out));

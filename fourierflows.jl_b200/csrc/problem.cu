@@ -401,6 +401,12 @@ int ffb_problem_sol(ffb_problem* p, void** sol, int64_t* n) {
   return FFB_OK;
 }
 
+int ffb_problem_plan(ffb_problem* p, ffb_plan** plan) {
+  FFB_REQUIRE(p && plan, FFB_EINVAL, "NULL argument");
+  *plan = p->plan;
+  return FFB_OK;
+}
+
 int ffb_problem_clock(ffb_problem* p, double* t, int64_t* step, double* dt) {
   FFB_REQUIRE(p, FFB_EINVAL, "prob is NULL");
   if (t) *t = p->t;

@@ -88,6 +88,31 @@ class Dist:
             self._h = None
 
 
+def enable_p2p(plan_handle, dist: "Dist"):
+    """Exchange the IPC handles of a plan's two receive buffers over torch.distributed and hand the mapped peer pointers to
+    the plan (`ffb_plan_dist_set_peers`)."""
+    import torch.distributed as td
+    b0, b1, nb = C.c_void_p(), C.c_void_p(), C.c_size_t()
+    L.call("ffb_plan_dist_recv_buffers", plan_handle, C.byref(b0), C.byref(b1), C.byref(nb))
+    h0, h1 = C.create_string_buffer(64), C.create_string_buffer(64)
+    L.call("ffb_dist_ipc_export", b0, h0)
+    L.call("ffb_dist_ipc_export", b1, h1)
+    gathered = [None] * dist.nranks
+    td.all_gather_object(gathered, (h0.raw, h1.raw))
+    P = dist.nranks
+    p0, p1 = (C.c_void_p * P)(), (C.c_void_p * P)()
+    for r in range(P):
+        if r == dist.rank:
+            p0[r], p1[r] = b0.value, b1.value
+        else:
+            q0, q1 = C.c_void_p(), C.c_void_p()
+            L.call("ffb_dist_ipc_open", C.create_string_buffer(gathered[r][0], 64), C.byref(q0))
+            L.call("ffb_dist_ipc_open", C.create_string_buffer(gathered[r][1], 64), C.byref(q1))
+            p0[r], p1[r] = q0.value, q1.value
+    L.call("ffb_plan_dist_set_peers", plan_handle, p0, p1)
+    td.barrier()
+
+
 class DistPlan:
     """Slab-decomposed `rfftplan` of a 3-D grid: `mul(out, a)` / `ldiv(out, ah)` on the local slabs."""
 
@@ -107,6 +132,12 @@ class DistPlan:
         buf = C.create_string_buffer(512)
         L.call("ffb_plan_describe", self._h, buf, 512)
         return buf.value.decode()
+
+    def enable_p2p(self):
+        """Fused pass + collective: map every peer's receive buffers (CUDA IPC over NVLink) so that the pass before the
+        exchange stores straight into them.  Collective call: every rank of the torch.distributed group must make it."""
+        enable_p2p(self._h, self.dist)
+        return self
 
     def mul(self, out: DevArray, a: DevArray):
         L.call("ffb_fft_forward", self._h, a.ptr, out.ptr)

@@ -138,6 +138,16 @@ int ffb_dist_destroy(ffb_dist* dist);
 int ffb_dist_info(const ffb_dist* dist, int* rank, int* nranks);
 int ffb_dist_alltoall(ffb_dist* dist, const void* sendbuf, void* recvbuf, size_t block_bytes);
 int ffb_plan_create_dist(ffb_plan** plan, int ndim, const int64_t* n, int dtype, ffb_dist* dist, int nchunks /* 0 = default */);
+/* Fused pass + collective: the strided pass before the exchange stores its output straight into the peers' receive
+ * buffers over NVLink (buffers mapped through CUDA IPC), so the all-to-all disappears and one stream-ordered barrier
+ * remains.  Setup: each rank asks its plan for its two receive buffers, exports their IPC handles, the launcher gathers
+ * them, every rank opens its peers' handles and hands the mapped pointers (own rank: its local buffer) to the plan. */
+int ffb_plan_dist_recv_buffers(ffb_plan* plan, void** buf0, void** buf1, size_t* bytes_each);
+int ffb_plan_dist_set_peers(ffb_plan* plan, void* const* peers_buf0, void* const* peers_buf1);   /* arrays of nranks pointers */
+int ffb_dist_ipc_export(void* dev_ptr, void* host_handle64);
+int ffb_dist_ipc_open(const void* host_handle64, void** dev_ptr);
+int ffb_dist_ipc_close(void* dev_ptr);
+int ffb_dist_barrier(ffb_dist* dist);
 
 /* ---------------------------------------------------------------- grid-side kernels (src/domains.jl)
  * wavenumber vectors `k, l, m, kr` (:77-78,193-195,333-336): fftfreq/rfftfreq computed in Float64, stored as T. */
@@ -242,6 +252,7 @@ typedef struct {
 int ffb_problem_create(ffb_problem** prob, const ffb_problem_config* cfg);
 int ffb_problem_destroy(ffb_problem* prob);
 int ffb_problem_sol(ffb_problem* prob, void** sol, int64_t* n_complex);   /* device pointer of `prob.sol` */
+int ffb_problem_plan(ffb_problem* prob, ffb_plan** plan);                 /* `prob.grid.rfftplan` (borrowed handle) */
 int ffb_problem_clock(ffb_problem* prob, double* t, int64_t* step, double* dt);
 int ffb_problem_set_dt(ffb_problem* prob, double dt);
 int ffb_problem_bytes(ffb_problem* prob, size_t* device_bytes);
