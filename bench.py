@@ -27,6 +27,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+EXCHANGE = "copy-engine"
 P2P = 1             # N > 1: fused pass + collective exchange (--no-p2p falls back to the chunked NCCL all-to-all)
 FUSED = 1           # fold calcN!'s spectral multiplies / products / dealias into the FFT passes (--no-fuse disables)
 NVLINK_GBS = 770.0  # measured peer copy per direction per GPU (B200_PROFILING.md)
@@ -119,13 +120,13 @@ class Burgers3D:
         rng = np.random.default_rng(1234 + rank)
         sl = rng.standard_normal(prob.physical_shape, dtype=np.float32)
         if P2P and comm is not None:
-            prob.enable_p2p()   # fused pass + collective: peer stores over NVLink instead of the NCCL all-to-all
+            prob.enable_p2p(EXCHANGE)   # exchange through IPC-mapped peer memory over NVLink instead of the NCCL all-to-all
         prob.set_physical(np.asfortranarray(0.1 * sl))
         return prob
 
     def fft_plan(self, ff, L, comm):
         plan = ff.DistPlan(self.shape, self.T, comm)
-        return plan.enable_p2p() if P2P else plan
+        return plan.enable_p2p(EXCHANGE) if P2P else plan
 
     def make_cpu(self, fo, n_sample):
         prob = fo.Burgers3D.Problem(nx=n_sample, kappa=self.kappa, dt=self.dt, stepper="ETDRK4", T=self.T)
@@ -327,7 +328,7 @@ def run_gpu(args):
         "scaling": "weak" if world > 1 else "strong", "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic",
         "config": {"workload": wl.name, "grid": list(wl.shape), "stepper": "ETDRK4", "parallelism": wl.parallelism,
                    "l2": "every array is far larger than the 126 MB L2; no flush needed", "device_bytes_per_gpu": dev_bytes,
-                   "calcN_fusion": bool(FUSED) and world == 1, "exchange": ("peer stores over NVLink fused into the FFT pass + barrier" if P2P else "chunked NCCL all-to-all") if world > 1 and wl.replicas == 1 else None},
+                   "calcN_fusion": bool(FUSED) and world == 1, "exchange": {"peer-store": "peer stores over NVLink fused into the FFT pass + barrier", "copy-engine": "chunked copy-engine pushes into IPC-mapped peer buffers over NVLink, overlapped with the next chunk's pass", "nccl": "chunked NCCL all-to-all"}[EXCHANGE if P2P else "nccl"] if world > 1 and wl.replicas == 1 else None},
         "step_roofline": {"algorithmic_hbm_bytes_per_step": total_bytes, "nvlink_bytes_per_gpu_per_step": nvlink_bytes,
                           "hbm_ms_at_peak": hbm_ms, "nvlink_ms_at_770": nvl_ms, "ms_at_roofline_overlapped": max(hbm_ms, nvl_ms),
                           "frac": max(hbm_ms, nvl_ms) / ms_per_step, "frac_non_overlapped": (hbm_ms + nvl_ms) / ms_per_step,
@@ -364,12 +365,15 @@ def main():
     ap.add_argument("--nz-per-gpu", type=int, default=256, help="C5 z-planes per GPU (weak scaling; 256 x 8 = 2048)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="grid size of the cpu_baseline sample (default 4096 for C3)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-p2p", action="store_true", help="N > 1: use the chunked NCCL all-to-all instead of peer stores")
+    ap.add_argument("--no-p2p", action="store_true", help="N > 1: same as --exchange nccl")
+    ap.add_argument("--exchange", default="copy-engine", choices=["nccl", "peer-store", "copy-engine"],
+                    help="N > 1: how the slab transpose moves data between GPUs")
     ap.add_argument("--no-fuse", action="store_true", help="run calcN! as separate elementwise kernels (the byte model of SURVEY 8d)")
     args = ap.parse_args()
-    global FUSED, P2P
+    global FUSED, P2P, EXCHANGE
     FUSED = 0 if args.no_fuse else 1
-    P2P = 0 if args.no_p2p else 1
+    EXCHANGE = args.exchange
+    P2P = 0 if (args.no_p2p or EXCHANGE == "nccl") else 1
     if args.impl == "reference":
         run_reference(args)
     else:

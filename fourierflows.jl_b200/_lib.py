@@ -98,6 +98,7 @@ SIGNATURES = {
     "ffb_plan_create_dist": [_P(_vp), _i, _P(_i64), _i, _vp, _i],
     "ffb_plan_dist_recv_buffers": [_vp, _P(_vp), _P(_vp), _P(_sz)],
     "ffb_plan_dist_set_peers": [_vp, _P(_vp), _P(_vp)],
+    "ffb_plan_dist_set_exchange": [_vp, _i],
     "ffb_dist_ipc_export": [_vp, _vp],
     "ffb_dist_ipc_open": [_vp, _P(_vp)],
     "ffb_dist_ipc_close": [_vp],

@@ -68,12 +68,12 @@ class CProblem:
         L.call("ffb_problem_clock", self._h, C.byref(t), C.byref(step), C.byref(dt))
         return t.value, step.value, dt.value
 
-    def enable_p2p(self):
-        """slab-decomposed problems: fused pass + collective exchange (collective call on every rank)"""
+    def enable_p2p(self, mode: str = "peer-store"):
+        """slab-decomposed problems: exchange through peer memory, see `DistPlan.enable_p2p` (collective call on every rank)"""
         from .dist import enable_p2p
         ph = C.c_void_p()
         L.call("ffb_problem_plan", self._h, C.byref(ph))
-        enable_p2p(ph, self.dist)
+        enable_p2p(ph, self.dist, mode)
         return self
 
     def device_bytes(self):

@@ -2,6 +2,7 @@
 // docs/src/gpu.md:57): there is no reference counterpart; this is new capability named by BASELINE.json north_star.
 #include <dlfcn.h>
 #include <cstring>
+#include <cstdlib>
 #include "dist.h"
 #include "ffb_common.cuh"
 
@@ -83,6 +84,27 @@ int dist_alltoall_bytes(ffb_dist* d, const void* sendbuf, void* recvbuf, size_t 
   return FFB_OK;
 }
 
+int dist_push_blocks(ffb_dist* d, const void* sendbuf, void* const* peer_bufs, size_t dst_off, size_t count, size_t stride, cudaStream_t after) {
+  const char* sb = reinterpret_cast<const char*>(sendbuf);
+  if (after) {
+    cudaEvent_t e = dist_next_event(d);
+    FFB_CUDA(cudaEventRecord(e, after));
+    for (int k = 0; k < d->ncopy; ++k) FFB_CUDA(cudaStreamWaitEvent(d->copy_streams[k], e, 0));
+  }
+  // staggered destinations: at step i every rank writes to a different peer
+  for (int i = 0; i < d->nranks; ++i) {
+    const int to = (d->rank + i) % d->nranks;
+    FFB_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(peer_bufs[to]) + dst_off, sb + (size_t)to * stride, count, cudaMemcpyDeviceToDevice,
+                             d->copy_streams[i % d->ncopy]));
+  }
+  for (int k = 0; k < d->ncopy; ++k) {
+    cudaEvent_t e = dist_next_event(d);
+    FFB_CUDA(cudaEventRecord(e, d->copy_streams[k]));
+    FFB_CUDA(cudaStreamWaitEvent(d->comm_stream, e, 0));
+  }
+  return FFB_OK;
+}
+
 }  // namespace ffb
 
 using namespace ffb;
@@ -109,6 +131,9 @@ int ffb_dist_init(ffb_dist** out, int rank, int nranks, const void* id128) {
   if (r != 0) { delete d; return set_error(FFB_ENCCL, "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); }
   FFB_CUDA(cudaStreamCreateWithFlags(&d->comm_stream, cudaStreamNonBlocking));
   for (auto& e : d->ev) FFB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  d->ncopy = 4;
+  if (const char* e = getenv("FFB_COPY_STREAMS")) { const int v = atoi(e); if (v >= 1 && v <= 4) d->ncopy = v; }
+  for (auto& cs : d->copy_streams) FFB_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
   FFB_CUDA(cudaMalloc(&d->barrier_buf, 256));
   FFB_CUDA(cudaMemset(d->barrier_buf, 0, 256));
   *out = d;
@@ -120,6 +145,7 @@ int ffb_dist_destroy(ffb_dist* d) {
   cudaStreamSynchronize(d->comm_stream);
   if (d->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(d->comm);
   for (auto& e : d->ev) cudaEventDestroy(e);
+  for (auto& cs : d->copy_streams) { cudaStreamSynchronize(cs); cudaStreamDestroy(cs); }
   cudaStreamDestroy(d->comm_stream);
   cudaFree(d->barrier_buf);
   delete d;

@@ -11,6 +11,8 @@ struct ffb_dist {
   cudaEvent_t ev[64];      // ring of events for compute <-> comm ordering
   int ev_next;
   float* barrier_buf;      // device scratch of the barrier all-reduce
+  cudaStream_t copy_streams[4];   // copy-engine exchange: peer copies are spread over these streams
+  int ncopy;
 };
 
 namespace ffb {
@@ -21,4 +23,8 @@ cudaEvent_t dist_next_event(ffb_dist* d);
 // stream-ordered barrier across all ranks (1-element NCCL all-reduce): every rank's earlier work on `st` has completed
 // (including its stores into peer memory) before any rank's later work starts
 int dist_barrier(ffb_dist* d, cudaStream_t st);
+// copy-engine exchange (push): once the work already enqueued on `after` has finished (nullptr: no dependency), block s of
+// sendbuf (count bytes at sendbuf + s*stride_bytes) is copied into peer s's buffer at peer_bufs[s] + dst_off -- cudaMemcpyAsync
+// over NVLink, no SM involved.  d->comm_stream is made to wait for all of the copies (follow with dist_barrier on it).
+int dist_push_blocks(ffb_dist* d, const void* sendbuf, void* const* peer_bufs, size_t dst_off, size_t count, size_t stride_bytes, cudaStream_t after);
 }  // namespace ffb

@@ -13,6 +13,8 @@
 #include "dist.h"
 #include "fft_cluster.cuh"
 #include "fft_cluster_dispatch.h"
+#include "fft_stream.cuh"
+#include "fft_stream_dispatch.h"
 
 namespace ffb {
 
@@ -87,7 +89,7 @@ struct ffb_plan {
   // fused pass + collective: double-buffered receive buffers and their peer mappings (CUDA IPC)
   void* recv[2];
   void* peers[2][8];
-  bool p2p;
+  int p2p;                 // exchange mode (FFB_EXCHANGE_*)
   int p2p_cur;
 };
 
@@ -216,8 +218,8 @@ static int call_pow2(int N, int mode, int dir, const Pow2Params<T>& p, int gx, i
 
 // Lines-per-CTA choice (measured: tools/sweep_w.py, tools/sweep2.py, profiles/r01_sweep_*.log).  Throughput is set by how
 // many independent CTAs an SM can overlap, so CTAs are kept small.  ROWS: one line per CTA (>= 32 threads).
-// COLS: about 256 threads with W adjacent columns clamped to [64 B, 256 B] wide rows (Float64 4..16, Float32 8..32
-// columns; the twiddled four-step sub-pass likes 32).
+// COLS: about 256 threads with W adjacent columns clamped to [64 B, 256 B] wide rows (Float64 4..16, Float32 16..32
+// columns, 8 only when 16 do not fit -- N = 2048; the twiddled four-step sub-pass likes 32).
 template <typename T>
 static int choose_w(int N, int mode, long long nlines) {
   const int R = pow2_points_per_thread(N);
@@ -227,7 +229,7 @@ static int choose_w(int N, int mode, long long nlines) {
   const bool cols = (mode == C2C_COLS || mode == C2C_COLS_TW);
   int W = 1;
   if (cols) {
-    const int lo = sizeof(T) == 8 ? 4 : 8, hi = (sizeof(T) == 8 && mode == C2C_COLS) ? 16 : 32;
+    const int lo = sizeof(T) == 8 ? 4 : 16, hi = (sizeof(T) == 8 && mode == C2C_COLS) ? 16 : 32;   // Float32: 128-byte rows when the tile fits
     int want = std::max(lo, std::min(hi, 256 / std::max(Tn, 1)));
     while (W < want && Tn * W * 2 <= maxT && pow2_smem_bytes<T>(N, W * 2, mode) <= smem_cap) W *= 2;
   } else {
@@ -255,6 +257,52 @@ struct SegStride { int seg = 0; long long stride = 0; };  // seg = 0: unsegmente
 // two-level outer index (four-step sub-passes): blockIdx.y = o_lo + mod*o_hi -> o_lo*os + o_hi*os2
 struct Outer2 { int mod = 0; long long nhi = 1, in_os2 = 0, out_os2 = 0; };
 
+// Streaming kernel thresholds (measured, profiles/r01_stream_*.log); FFB_STREAM_MIN overrides (0 = never)
+static int stream_min_n(size_t real_bytes) {
+  if (const char* e = getenv("FFB_STREAM_MIN")) { const int v = atoi(e); return v > 0 ? v : (1 << 30); }
+  (void)real_bytes;
+  return 1 << 30;   // measured slower than the plain kernel (the passes are issue-bound, not latency-bound): opt-in only
+}
+
+template <typename T>
+static int stream_pass(int N, int dir, const void* in, void* out, long long in_es, long long in_os, long long out_es, long long out_os,
+                       long long nlines, long long nouter, T scale, const cx<T>* tw, cudaStream_t st, SegStride in_seg, SegStride out_seg) {
+  StreamParams<T> p;
+  const int Tn = N / 16;
+  const int maxT = pow2_max_threads(sizeof(T));
+  int W = std::min(sizeof(T) == 8 ? 8 : 16, maxT / Tn);
+  if (const char* e = getenv("FFB_W_STREAM")) { const int w = atoi(e); if (w >= 1 && is_pow2((uint64_t)w) && Tn * w <= maxT) W = w; }
+  while (W > 1 && W / 2 >= nlines) W /= 2;
+  const size_t cap = (size_t)max_smem_optin() - 1024;
+  int split = 1;
+  if constexpr (sizeof(T) == 4) {
+    split = stream_smem_bytes<T, false>(N, W) > cap;
+    if (const char* e = getenv("FFB_STREAM_SPLIT")) split = atoi(e) != 0 || split;
+  }
+  const size_t smem = split ? stream_smem_bytes<T, true>(N, W) : stream_smem_bytes<T, false>(N, W);
+  FFB_REQUIRE(smem <= cap, FFB_EUNSUPPORTED, "streaming pass N=%d W=%d needs %zu bytes of shared memory", N, W, smem);
+  p.in = reinterpret_cast<const cx<T>*>(in); p.out = reinterpret_cast<cx<T>*>(out);
+  p.in_es = in_es; p.in_os = in_os; p.out_es = out_es; p.out_os = out_os;
+  for (int m = 0; m < 16; ++m) {
+    const long long i = (long long)m * Tn;
+    p.in_off[m] = in_seg.seg ? (i % in_seg.seg) * in_es + (i / in_seg.seg) * in_seg.stride : i * in_es;
+    p.out_off[m] = out_seg.seg ? (i % out_seg.seg) * out_es + (i / out_seg.seg) * out_seg.stride : i * out_es;
+  }
+  p.nlines = nlines; p.W = W;
+  const long long gx = (nlines + W - 1) / W;
+  FFB_REQUIRE(gx < (1ll << 31), FFB_EUNSUPPORTED, "too many lines for one launch");
+  p.gx = (int)gx; p.ntiles = gx * nouter;
+  p.scale = scale; p.tw = tw; p.keep_out = g_pass_keep;
+  char pname[64];
+  snprintf(pname, sizeof(pname), "fft_c2c_cols_stream_%s_N%d", sizeof(T) == 8 ? "f64" : "f32", N);
+  ProfScope ps(pname, (double)nlines * (double)nouter * 2.0 * N * sizeof(cx<T>));
+  int rc;
+  if constexpr (sizeof(T) == 8) rc = stream_launch_double(N, dir, split, &p, Tn * W, smem, st);
+  else rc = stream_launch_float(N, dir, split, &p, Tn * W, smem, st);
+  if (rc == 1) return set_error(FFB_EUNSUPPORTED, "no streaming FFT kernel for N=%d", N);
+  return rc;
+}
+
 template <typename T>
 static int pow2_pass(int N, int mode, int dir, const void* in, void* out, long long in_es, long long in_ls, long long in_os,
                      long long out_es, long long out_ls, long long out_os, long long nlines, long long nouter, T scale,
@@ -270,6 +318,26 @@ static int pow2_pass(int N, int mode, int dir, const void* in, void* out, long l
     p.use_peer = 1;
     for (int q = 0; q < npeers; ++q) p.out_peer[q] = peer_out[q];
   }
+  // plain long strided passes: software-pipelined persistent kernel (fft_stream.cuh)
+  if (mode == C2C_COLS && !pro && !epi && !rmul && !peer_out && !o2.mod && in_ls == 1 && out_ls == 1 && stream_has(N) && N >= stream_min_n(sizeof(T))) {
+    const int Tn = N / 16;
+    const bool seg_ok = (!in_seg.seg || in_seg.seg % Tn == 0) && (!out_seg.seg || out_seg.seg % Tn == 0);
+    if (seg_ok) return stream_pass<T>(N, dir, in, out, in_es, in_os, out_es, out_os, nlines, nouter, scale, tw, st, in_seg, out_seg);
+  }
+  // plain strided passes: lean kernel variant with host-computed element offsets (needs segment lengths that are multiples of N/R)
+  static int lean_env = -1;
+  if (lean_env < 0) { const char* e = getenv("FFB_LEAN"); lean_env = e ? atoi(e) : 1; }
+  if (lean_env && mode == C2C_COLS && !pro && !epi && !rmul && !peer_out && !o2.mod && in_ls == 1 && out_ls == 1 && !g_pass_reverse) {
+    const int R0 = pow2_points_per_thread(N), Tn = N / R0;
+    if ((!in_seg.seg || in_seg.seg % Tn == 0) && (!out_seg.seg || out_seg.seg % Tn == 0)) {
+      mode = C2C_COLS_LEAN;
+      for (int m = 0; m < 16; ++m) {
+        const long long i = (long long)m * Tn;
+        p.in_off[m] = in_seg.seg ? (i % in_seg.seg) * in_es + (i / in_seg.seg) * in_seg.stride : i * in_es;
+        p.out_off[m] = out_seg.seg ? (i % out_seg.seg) * out_es + (i / out_seg.seg) * out_seg.stride : i * out_es;
+      }
+    }
+  }
   if (pro) p.pro = *pro; else p.pro.on = 0;
   if (epi) p.epi = *epi; else p.epi.on = 0;
   p.rmul = rmul;
@@ -283,6 +351,12 @@ static int pow2_pass(int N, int mode, int dir, const void* in, void* out, long l
     // measured (tools/sweep3.py): +10 % for the Float64 r2c pass of 4096-point lines at one wave ahead, neutral or negative elsewhere
     p.pf_ahead = pf_env >= 0 ? pf_env : ((mode == R2C_ROWS && N * sizeof(cx<T>) >= 32768) ? num_sms() : 0);
   }
+  if (mode == C2C_COLS_LEAN) {
+    // measured (tools/stream_sweep.py): +5 % when the tile fills the SM (one CTA per SM), -20 % when several CTAs share an SM
+    static int pfc = -2;
+    if (pfc == -2) { const char* e = getenv("FFB_PF_COLS"); pfc = e ? atoi(e) : -1; }
+    p.pf_ahead = pfc >= 0 ? pfc : -1;   // resolved below once the tile shape is known
+  }
   p.in_seg_mask = in_seg.seg ? in_seg.seg - 1 : 0x7fffffff; p.in_seg_shift = in_seg.seg ? ilog2((uint64_t)in_seg.seg) : 31;
   p.in_seg_stride = in_seg.stride;
   p.out_seg_mask = out_seg.seg ? out_seg.seg - 1 : 0x7fffffff; p.out_seg_shift = out_seg.seg ? ilog2((uint64_t)out_seg.seg) : 31;
@@ -292,16 +366,17 @@ static int pow2_pass(int N, int mode, int dir, const void* in, void* out, long l
   p.in_os2 = o2.in_os2; p.out_os2 = o2.out_os2;
   p.twN = twN; p.twN_mask = twN_mask;
   p.nlines = nlines;
-  p.W = choose_w<T>(N, mode, nlines);
+  p.W = choose_w<T>(N, mode == C2C_COLS_LEAN ? C2C_COLS : mode, nlines);
   p.scale = scale;
   p.tw = tw;
   p.twr = twr;
   const int R = pow2_points_per_thread(N);
   const int threads = (N / R) * p.W;
+  if (mode == C2C_COLS_LEAN && p.pf_ahead < 0) p.pf_ahead = threads >= pow2_max_threads(sizeof(T)) ? num_sms() : 0;
   const size_t smem = pow2_smem_bytes<T>(N, p.W, mode);
   const long long gx = (nlines + p.W - 1) / p.W;
   FFB_REQUIRE(gx < (1ll << 31), FFB_EUNSUPPORTED, "too many lines for one launch");
-  static const char* mode_names[5] = {"c2c_rows", "c2c_cols", "r2c_rows", "c2r_rows", "c2c_cols_tw"};
+  static const char* mode_names[6] = {"c2c_rows", "c2c_cols", "r2c_rows", "c2r_rows", "c2c_cols_tw", "c2c_cols"};
   char pname[64];
   snprintf(pname, sizeof(pname), "fft_%s_%s_N%d", mode_names[mode], sizeof(T) == 8 ? "f64" : "f32", N);
   // algorithmic bytes: every element of the line set is read once and written once
@@ -645,6 +720,45 @@ static int exec_dist(ffb_plan* pl, const void* in, void* out, int dir) {
   long double tot = (long double)pl->n[0] * ny * nz;
   const T inv = (T)(1.0L / tot);
   SegStride seg; seg.seg = (int)nyl; seg.stride = blk;
+  if (pl->p2p == 2) {
+    // ---- copy-engine exchange: each pass writes its z-chunk in destination-rank-major order (as for NCCL); the blocks are
+    //      pushed into the peers' receive buffers with cudaMemcpyAsync over NVLink (no SM, runs beside the next chunk's pass);
+    //      a one-element all-reduce on the communication stream tells the receiver that a chunk has landed everywhere ----
+    const int cur = pl->p2p_cur;
+    pl->p2p_cur ^= 1;
+    cx<T>* mine = reinterpret_cast<cx<T>*>(pl->recv[cur]);
+    const size_t esz = sizeof(cx<T>);
+    if (dir < 0) {
+      if ((rc = pow2_pass<T>(N0, R2C_ROWS, -1, in, w0, 1, N0, 0, 1, nkr, 0, ny * nzl, 1, T(1), tb0->tw, tb0->twr, st))) return rc;
+      for (int c = 0; c < nch; ++c) {
+        if ((rc = pow2_pass<T>((int)ny, C2C_COLS, -1, w0 + c * zc * nkr * ny, w1 + c * sub, nkr, 1, nkr * ny, nkr, 1, nkr * nyl, nkr, zc, T(1), tb1->tw,
+                               nullptr, st, SegStride(), seg))) return rc;
+        if ((rc = dist_push_blocks(d, w1 + c * sub, pl->peers[cur], ((size_t)d->rank * blk + (size_t)c * sub) * esz, (size_t)sub * esz, (size_t)blk * esz, st))) return rc;
+      }
+      if ((rc = dist_barrier(d, d->comm_stream))) return rc;
+      cudaEvent_t e = dist_next_event(d);
+      FFB_CUDA(cudaEventRecord(e, d->comm_stream));
+      FFB_CUDA(cudaStreamWaitEvent(st, e, 0));
+      return pow2_pass<T>((int)nz, C2C_COLS, -1, mine, out, nkr * nyl, 1, 0, nkr * nyl, 1, 0, nkr * nyl, 1, T(1), tb2->tw, nullptr, st);
+    }
+    if ((rc = pow2_pass<T>((int)nz, C2C_COLS, +1, in, w0, nkr * nyl, 1, 0, nkr * nyl, 1, 0, nkr * nyl, 1, T(1), tb2->tw, nullptr, st))) return rc;
+    cudaEvent_t landed[8];
+    for (int c = 0; c < nch; ++c) {
+      if ((rc = dist_push_blocks(d, w0 + c * sub, pl->peers[cur], ((size_t)d->rank * blk + (size_t)c * sub) * esz, (size_t)sub * esz, (size_t)blk * esz,
+                                 c == 0 ? st : nullptr))) return rc;
+      if ((rc = dist_barrier(d, d->comm_stream))) return rc;
+      landed[c] = dist_next_event(d);   // ring of 64 events, at most 6 per chunk: no wrap-around before the wait below
+      FFB_CUDA(cudaEventRecord(landed[c], d->comm_stream));
+    }
+    for (int c = 0; c < nch; ++c) {
+      FFB_CUDA(cudaStreamWaitEvent(st, landed[c], 0));
+      if ((rc = pow2_pass<T>((int)ny, C2C_COLS, +1, mine + c * sub, w2 + c * zc * nkr * ny, nkr, 1, nkr * nyl, nkr, 1, nkr * ny, nkr, zc, T(1), tb1->tw, nullptr, st,
+                             seg, SegStride()))) return rc;
+      if ((rc = pow2_pass<T>(N0, C2R_ROWS, +1, w2 + c * zc * nkr * ny, reinterpret_cast<cx<T>*>(out) + c * zc * (long long)N0 * ny, 1, nkr, 0, 1, N0, 0,
+                             ny * zc, 1, inv, tb0->tw, tb0->twr, st))) return rc;
+    }
+    return FFB_OK;
+  }
   if (pl->p2p) {
     // ---- fused pass + collective: the pass before the exchange stores directly into the peers' receive buffers (NVLink),
     //      one stream-ordered barrier replaces the all-to-all; receive buffers are double-buffered across transforms ----
@@ -734,7 +848,7 @@ int ffb_plan_create(ffb_plan** out, int ndim, const int64_t* n, int dtype, int k
   auto* pl = new ffb_plan();
   pl->ndim = ndim; pl->dtype = dtype; pl->kind = kind; pl->nbatch = nbatch; pl->flags = flags;
   pl->dist = nullptr; pl->nyl = pl->nzl = 0; pl->nchunks = 1;
-  pl->recv[0] = pl->recv[1] = nullptr; pl->p2p = false; pl->p2p_cur = 0;
+  pl->recv[0] = pl->recv[1] = nullptr; pl->p2p = 0; pl->p2p_cur = 0;
   for (int b = 0; b < 2; ++b) for (int q = 0; q < 8; ++q) pl->peers[b][q] = nullptr;
   for (int d = 0; d < 3; ++d) { pl->n[d] = d < ndim ? n[d] : 1; pl->nc[d] = pl->n[d]; pl->tables[d] = nullptr; pl->ws[d] = nullptr; }
   if (kind == FFB_R2C) pl->nc[0] = pl->n[0] / 2 + 1;
@@ -791,8 +905,19 @@ int ffb_plan_dist_set_peers(ffb_plan* pl, void* const* peers0, void* const* peer
   }
   FFB_REQUIRE(pl->peers[0][pl->dist->rank] == pl->recv[0] && pl->peers[1][pl->dist->rank] == pl->recv[1], FFB_EINVAL,
               "the entry of the own rank must be the local receive buffer");
-  pl->p2p = true;
+  pl->p2p = 1;
   pl->desc += "peer-store-exchange ";
+  return FFB_OK;
+}
+
+int ffb_plan_dist_set_exchange(ffb_plan* pl, int mode) {
+  FFB_REQUIRE(pl && pl->dist, FFB_EINVAL, "needs a slab-decomposed plan");
+  FFB_REQUIRE(mode == FFB_EXCHANGE_NCCL || mode == FFB_EXCHANGE_PEER_STORE || mode == FFB_EXCHANGE_COPY_ENGINE, FFB_EINVAL, "bad exchange mode %d", mode);
+  FFB_REQUIRE(mode == FFB_EXCHANGE_NCCL || pl->peers[0][0], FFB_EINVAL, "call ffb_plan_dist_set_peers first");
+  FFB_REQUIRE(pl->nchunks <= 8, FFB_EUNSUPPORTED, "too many chunks");
+  pl->p2p = mode;
+  static const char* names[3] = {"exchange=nccl ", "exchange=peer-store ", "exchange=copy-engine "};
+  pl->desc += names[mode];
   return FFB_OK;
 }
 

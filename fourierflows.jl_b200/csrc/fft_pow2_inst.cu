@@ -39,6 +39,7 @@ static int launch_n(int mode, int dir, const Pow2Params<real_t>& p, dim3 grid, i
   switch (mode) {
     case C2C_ROWS: return dir < 0 ? launch_one<C2C_ROWS, -1, R, Rs...>(p, grid, threads, smem, st) : launch_one<C2C_ROWS, 1, R, Rs...>(p, grid, threads, smem, st);
     case C2C_COLS: return dir < 0 ? launch_one<C2C_COLS, -1, R, Rs...>(p, grid, threads, smem, st) : launch_one<C2C_COLS, 1, R, Rs...>(p, grid, threads, smem, st);
+    case C2C_COLS_LEAN: return dir < 0 ? launch_one<C2C_COLS_LEAN, -1, R, Rs...>(p, grid, threads, smem, st) : launch_one<C2C_COLS_LEAN, 1, R, Rs...>(p, grid, threads, smem, st);
     case C2C_COLS_TW:
       if constexpr (radix_product<Rs...>::value <= 256)
         return dir < 0 ? launch_one<C2C_COLS_TW, -1, R, Rs...>(p, grid, threads, smem, st) : launch_one<C2C_COLS_TW, 1, R, Rs...>(p, grid, threads, smem, st);

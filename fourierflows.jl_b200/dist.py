@@ -88,9 +88,13 @@ class Dist:
             self._h = None
 
 
-def enable_p2p(plan_handle, dist: "Dist"):
-    """Exchange the IPC handles of a plan's two receive buffers over torch.distributed and hand the mapped peer pointers to
-    the plan (`ffb_plan_dist_set_peers`)."""
+EXCHANGE = {"nccl": 0, "peer-store": 1, "copy-engine": 2}
+
+
+def enable_p2p(plan_handle, dist: "Dist", mode: str = "peer-store"):
+    """Exchange the IPC handles of a plan's two receive buffers over torch.distributed, hand the mapped peer pointers to
+    the plan (`ffb_plan_dist_set_peers`) and select the exchange (`ffb_plan_dist_set_exchange`):
+    "peer-store" = the pass before the exchange stores into the peers' buffers, "copy-engine" = chunked cudaMemcpyAsync pushes."""
     import torch.distributed as td
     b0, b1, nb = C.c_void_p(), C.c_void_p(), C.c_size_t()
     L.call("ffb_plan_dist_recv_buffers", plan_handle, C.byref(b0), C.byref(b1), C.byref(nb))
@@ -110,6 +114,7 @@ def enable_p2p(plan_handle, dist: "Dist"):
             L.call("ffb_dist_ipc_open", C.create_string_buffer(gathered[r][1], 64), C.byref(q1))
             p0[r], p1[r] = q0.value, q1.value
     L.call("ffb_plan_dist_set_peers", plan_handle, p0, p1)
+    L.call("ffb_plan_dist_set_exchange", plan_handle, EXCHANGE[mode])
     td.barrier()
 
 
@@ -133,10 +138,11 @@ class DistPlan:
         L.call("ffb_plan_describe", self._h, buf, 512)
         return buf.value.decode()
 
-    def enable_p2p(self):
-        """Fused pass + collective: map every peer's receive buffers (CUDA IPC over NVLink) so that the pass before the
-        exchange stores straight into them.  Collective call: every rank of the torch.distributed group must make it."""
-        enable_p2p(self._h, self.dist)
+    def enable_p2p(self, mode: str = "peer-store"):
+        """Map every peer's receive buffers (CUDA IPC over NVLink) and exchange through them: "peer-store" (the pass before
+        the exchange stores straight into them) or "copy-engine" (chunked cudaMemcpyAsync pushes beside the next chunk's pass).
+        Collective call: every rank of the torch.distributed group must make it."""
+        enable_p2p(self._h, self.dist, mode)
         return self
 
     def mul(self, out: DevArray, a: DevArray):

@@ -144,6 +144,12 @@ int ffb_plan_create_dist(ffb_plan** plan, int ndim, const int64_t* n, int dtype,
  * them, every rank opens its peers' handles and hands the mapped pointers (own rank: its local buffer) to the plan. */
 int ffb_plan_dist_recv_buffers(ffb_plan* plan, void** buf0, void** buf1, size_t* bytes_each);
 int ffb_plan_dist_set_peers(ffb_plan* plan, void* const* peers_buf0, void* const* peers_buf1);   /* arrays of nranks pointers */
+/* Exchange used by a slab-decomposed plan.  NCCL: chunked grouped send/recv (default, needs no peer mapping).
+ * PEER_STORE: the fused pass described above (selected by ffb_plan_dist_set_peers).  COPY_ENGINE: the passes write
+ * destination-major chunks and cudaMemcpyAsync pushes them into the peers' receive buffers while the next chunk is being
+ * transformed (no SM involved); a one-element all-reduce per chunk is the arrival barrier. */
+enum { FFB_EXCHANGE_NCCL = 0, FFB_EXCHANGE_PEER_STORE = 1, FFB_EXCHANGE_COPY_ENGINE = 2 };
+int ffb_plan_dist_set_exchange(ffb_plan* plan, int mode);
 int ffb_dist_ipc_export(void* dev_ptr, void* host_handle64);
 int ffb_dist_ipc_open(const void* host_handle64, void** dev_ptr);
 int ffb_dist_ipc_close(void* dev_ptr);

@@ -29,10 +29,10 @@ def main():
         rng = np.random.default_rng(5)
         x = np.asfortranarray(rng.standard_normal(shape).astype(T))
         ref = fo.RfftPlan(shape, T) * x.astype(np.float64)
-        for nch in (0, 1, -1):   # -1: fused pass + collective (peer stores over NVLink instead of the NCCL all-to-all)
+        for nch in (0, 1, -1, -2):   # -1: fused pass + collective (peer stores over NVLink), -2: copy-engine pushes
             plan = ff.DistPlan(shape, T, comm, nchunks=max(nch, 0))
             if nch < 0:
-                plan.enable_p2p()
+                plan.enable_p2p("peer-store" if nch == -1 else "copy-engine")
             xl = ff.DevArray.from_numpy(ff.physical_slab(x, P, rank))
             xh = plan * xl
             e1 = relerr(xh.to_numpy(), ff.spectral_slab(ref, P, rank))
@@ -54,7 +54,7 @@ def main():
         ob.grid.rfftplan.mul(ob.sol, c0)
         cp = ff.CProblem(n, 2 * np.pi, stepper=stepper, dt=1e-3, calcN="burgers3d", nu=1e-3, T=T, dist=comm)
         if stepper != "LSRK54":
-            cp.enable_p2p()
+            cp.enable_p2p("peer-store" if stepper == "ETDRK4" else "copy-engine")
         cp.set_physical(ff.physical_slab(c0, P, rank))
         for s in range(3):
             cp.stepforward(1)
