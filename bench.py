@@ -27,7 +27,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-EXCHANGE = "copy-engine"
+EXCHANGE = "auto"
 P2P = 1             # N > 1: fused pass + collective exchange (--no-p2p falls back to the chunked NCCL all-to-all)
 FUSED = 1           # fold calcN!'s spectral multiplies / products / dealias into the FFT passes (--no-fuse disables)
 NVLINK_GBS = 770.0  # measured peer copy per direction per GPU (B200_PROFILING.md)
@@ -328,7 +328,7 @@ def run_gpu(args):
         "scaling": "weak" if world > 1 else "strong", "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic",
         "config": {"workload": wl.name, "grid": list(wl.shape), "stepper": "ETDRK4", "parallelism": wl.parallelism,
                    "l2": "every array is far larger than the 126 MB L2; no flush needed", "device_bytes_per_gpu": dev_bytes,
-                   "calcN_fusion": bool(FUSED) and world == 1, "exchange": {"peer-store": "peer stores over NVLink fused into the FFT pass + barrier", "copy-engine": "chunked copy-engine pushes into IPC-mapped peer buffers over NVLink, overlapped with the next chunk's pass", "nccl": "chunked NCCL all-to-all"}[EXCHANGE if P2P else "nccl"] if world > 1 and wl.replicas == 1 else None},
+                   "calcN_fusion": bool(FUSED) and world == 1, "exchange": exchange_desc(prob, world, wl)},
         "step_roofline": {"algorithmic_hbm_bytes_per_step": total_bytes, "nvlink_bytes_per_gpu_per_step": nvlink_bytes,
                           "hbm_ms_at_peak": hbm_ms, "nvlink_ms_at_770": nvl_ms, "ms_at_roofline_overlapped": max(hbm_ms, nvl_ms),
                           "frac": max(hbm_ms, nvl_ms) / ms_per_step, "frac_non_overlapped": (hbm_ms + nvl_ms) / ms_per_step,
@@ -353,6 +353,18 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+def exchange_desc(prob, world, wl):
+    if world == 1 or wl.replicas != 1:
+        return None
+    names = {"peer-store": "peer stores over NVLink fused into the FFT pass (blocked receive layout) + barrier",
+             "copy-engine": "kx-chunked copy-engine pushes into IPC-mapped peer buffers over NVLink, overlapped with the neighbouring chunks' passes",
+             "nccl": "chunked NCCL all-to-all"}
+    used = getattr(prob, "exchange", "nccl") if P2P else "nccl"
+    import fourierflows_jl_b200 as ff
+    tuned = ff.dist.AUTOTUNE_LOG[:1] if EXCHANGE == "auto" else []   # first entry: the problem's plan
+    return {"used": used, "how": names[used], "requested": EXCHANGE, "autotune_ms_fwd_plus_inv": tuned[0]["ms"] if tuned else None}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -366,8 +378,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0, help="grid size of the cpu_baseline sample (default 4096 for C3)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-p2p", action="store_true", help="N > 1: same as --exchange nccl")
-    ap.add_argument("--exchange", default="copy-engine", choices=["nccl", "peer-store", "copy-engine"],
-                    help="N > 1: how the slab transpose moves data between GPUs")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "peer-store", "copy-engine"],
+                    help="N > 1: how the slab transpose moves data between GPUs (auto: measured at plan time, fastest kept)")
     ap.add_argument("--no-fuse", action="store_true", help="run calcN! as separate elementwise kernels (the byte model of SURVEY 8d)")
     args = ap.parse_args()
     global FUSED, P2P, EXCHANGE

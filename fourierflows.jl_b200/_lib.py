@@ -99,8 +99,8 @@ SIGNATURES = {
     "ffb_plan_dist_recv_buffers": [_vp, _P(_vp), _P(_vp), _P(_sz)],
     "ffb_plan_dist_set_peers": [_vp, _P(_vp), _P(_vp)],
     "ffb_plan_dist_set_exchange": [_vp, _i],
-    "ffb_dist_ipc_export": [_vp, _vp],
-    "ffb_dist_ipc_open": [_vp, _P(_vp)],
+    "ffb_dist_ipc_export": [_vp, _vp, _P(_sz)],
+    "ffb_dist_ipc_open": [_vp, _sz, _P(_vp)],
     "ffb_dist_ipc_close": [_vp],
     "ffb_dist_barrier": [_vp],
     "ffb_wavenumbers": [_vp, _i64, _d, _i, _i],

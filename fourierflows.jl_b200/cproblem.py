@@ -73,7 +73,7 @@ class CProblem:
         from .dist import enable_p2p
         ph = C.c_void_p()
         L.call("ffb_problem_plan", self._h, C.byref(ph))
-        enable_p2p(ph, self.dist, mode)
+        self.exchange = enable_p2p(ph, self.dist, mode, self.T, self.n)
         return self
 
     def device_bytes(self):

@@ -3,6 +3,9 @@
 #include <dlfcn.h>
 #include <cstring>
 #include <cstdlib>
+#include <cstdint>
+#include <mutex>
+#include <vector>
 #include "dist.h"
 #include "ffb_common.cuh"
 
@@ -129,10 +132,14 @@ int ffb_dist_init(ffb_dist** out, int rank, int nranks, const void* id128) {
   memcpy(id.internal, id128, 128);
   int r = reinterpret_cast<CommInitRankFn>(g_nccl.CommInitRank)(&d->comm, nranks, id, rank);
   if (r != 0) { delete d; return set_error(FFB_ENCCL, "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); }
-  FFB_CUDA(cudaStreamCreateWithFlags(&d->comm_stream, cudaStreamNonBlocking));
+  // the communication stream carries the arrival barriers (tiny NCCL kernels) and the NCCL exchange: highest priority so that
+  // its blocks are placed as soon as a compute CTA retires instead of after the running pass has drained
+  int prio_lo = 0, prio_hi = 0;
+  FFB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  FFB_CUDA(cudaStreamCreateWithPriority(&d->comm_stream, cudaStreamNonBlocking, prio_hi));
   for (auto& e : d->ev) FFB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-  d->ncopy = 4;
-  if (const char* e = getenv("FFB_COPY_STREAMS")) { const int v = atoi(e); if (v >= 1 && v <= 4) d->ncopy = v; }
+  d->ncopy = nranks < 8 ? (nranks > 1 ? nranks : 1) : 8;   // one stream (copy engine) per destination
+  if (const char* e = getenv("FFB_COPY_STREAMS")) { const int v = atoi(e); if (v >= 1 && v <= 8) d->ncopy = v; }
   for (auto& cs : d->copy_streams) FFB_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
   FFB_CUDA(cudaMalloc(&d->barrier_buf, 256));
   FFB_CUDA(cudaMemset(d->barrier_buf, 0, 256));
@@ -159,27 +166,70 @@ int ffb_dist_info(const ffb_dist* d, int* rank, int* nranks) {
   return FFB_OK;
 }
 
-// CUDA IPC plumbing for the fused pass + collective path: a rank exports the handle of one of its buffers (64 bytes), the
-// launcher moves it to the other ranks, which map it (peer access is enabled lazily).
-int ffb_dist_ipc_export(void* dev_ptr, void* host_handle64) {
-  FFB_REQUIRE(dev_ptr && host_handle64, FFB_EINVAL, "NULL argument");
+// CUDA IPC plumbing for the exchanges through peer memory: a rank exports the handle of the ALLOCATION that holds one of its
+// buffers (64 bytes) plus the buffer's offset inside it (cudaMalloc sub-allocates small requests from shared blocks), the
+// launcher moves both to the other ranks, which map the allocation once (cache keyed by the handle bytes, reference counted;
+// opening the same allocation twice in one process fails with "resource already mapped") and add the offset.
+namespace {
+struct IpcMapping { char handle[64]; char* base; int refs; };
+std::vector<IpcMapping> g_ipc;
+std::mutex g_ipc_mu;
+typedef int (*MemGetAddressRangeFn)(unsigned long long*, size_t*, unsigned long long);
+}  // namespace
+
+int ffb_dist_ipc_export(void* dev_ptr, void* host_handle64, size_t* offset) {
+  FFB_REQUIRE(dev_ptr && host_handle64 && offset, FFB_EINVAL, "NULL argument");
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "unexpected IPC handle size");
+  char* base = reinterpret_cast<char*>(dev_ptr);
+  static MemGetAddressRangeFn get_range = nullptr;
+  static bool looked_up = false;
+  if (!looked_up) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+      get_range = reinterpret_cast<MemGetAddressRangeFn>(fn);
+    else cudaGetLastError();
+    looked_up = true;
+  }
+  if (get_range) {
+    unsigned long long b = 0; size_t sz = 0;
+    if (get_range(&b, &sz, (unsigned long long)(uintptr_t)dev_ptr) == 0 && b) base = reinterpret_cast<char*>((uintptr_t)b);
+  }
   cudaIpcMemHandle_t h;
-  FFB_CUDA(cudaIpcGetMemHandle(&h, dev_ptr));
+  FFB_CUDA(cudaIpcGetMemHandle(&h, base));
   memcpy(host_handle64, &h, 64);
+  *offset = (size_t)(reinterpret_cast<char*>(dev_ptr) - base);
   return FFB_OK;
 }
 
-int ffb_dist_ipc_open(const void* host_handle64, void** dev_ptr) {
+int ffb_dist_ipc_open(const void* host_handle64, size_t offset, void** dev_ptr) {
   FFB_REQUIRE(dev_ptr && host_handle64, FFB_EINVAL, "NULL argument");
+  std::lock_guard<std::mutex> lk(g_ipc_mu);
+  for (auto& m : g_ipc)
+    if (memcmp(m.handle, host_handle64, 64) == 0) { ++m.refs; *dev_ptr = m.base + offset; return FFB_OK; }
   cudaIpcMemHandle_t h;
   memcpy(&h, host_handle64, 64);
-  FFB_CUDA(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  void* base = nullptr;
+  FFB_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+  IpcMapping m;
+  memcpy(m.handle, host_handle64, 64);
+  m.base = reinterpret_cast<char*>(base); m.refs = 1;
+  g_ipc.push_back(m);
+  *dev_ptr = m.base + offset;
   return FFB_OK;
 }
 
 int ffb_dist_ipc_close(void* dev_ptr) {
-  if (dev_ptr) FFB_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+  if (!dev_ptr) return FFB_OK;
+  std::lock_guard<std::mutex> lk(g_ipc_mu);
+  int best = -1;   // the mapping with the greatest base <= dev_ptr (mapped allocations do not overlap)
+  for (int i = 0; i < (int)g_ipc.size(); ++i)
+    if (g_ipc[i].base <= reinterpret_cast<char*>(dev_ptr) && (best < 0 || g_ipc[i].base > g_ipc[best].base)) best = i;
+  FFB_REQUIRE(best >= 0, FFB_EINVAL, "pointer was not returned by ffb_dist_ipc_open");
+  if (--g_ipc[best].refs == 0) {
+    FFB_CUDA(cudaIpcCloseMemHandle(g_ipc[best].base));
+    g_ipc.erase(g_ipc.begin() + best);
+  }
   return FFB_OK;
 }
 

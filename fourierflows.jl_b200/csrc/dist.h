@@ -11,7 +11,7 @@ struct ffb_dist {
   cudaEvent_t ev[64];      // ring of events for compute <-> comm ordering
   int ev_next;
   float* barrier_buf;      // device scratch of the barrier all-reduce
-  cudaStream_t copy_streams[4];   // copy-engine exchange: peer copies are spread over these streams
+  cudaStream_t copy_streams[8];   // copy-engine exchange: peer copies are spread over these streams
   int ncopy;
 };
 

@@ -90,6 +90,7 @@ struct ffb_plan {
   void* recv[2];
   void* peers[2][8];
   int p2p;                 // exchange mode (FFB_EXCHANGE_*)
+  size_t recv_bytes;       // size of each receive buffer
   int p2p_cur;
 };
 
@@ -308,33 +309,26 @@ static int pow2_pass(int N, int mode, int dir, const void* in, void* out, long l
                      long long out_es, long long out_ls, long long out_os, long long nlines, long long nouter, T scale,
                      const cx<T>* tw, const cx<T>* twr, cudaStream_t st, SegStride in_seg = SegStride(), SegStride out_seg = SegStride(),
                      Outer2 o2 = Outer2(), const cx<T>* twN = nullptr, int twN_mask = 0,
-                     const typename Pow2Params<T>::Fuse* pro = nullptr, const typename Pow2Params<T>::Fuse* epi = nullptr, const T* rmul = nullptr,
-                     cx<T>* const* peer_out = nullptr, int npeers = 0) {
+                     const typename Pow2Params<T>::Fuse* pro = nullptr, const typename Pow2Params<T>::Fuse* epi = nullptr, const T* rmul = nullptr) {
   Pow2Params<T> p;
-  p.use_peer = 0;
-  for (int q = 0; q < 8; ++q) p.out_peer[q] = nullptr;
-  if (peer_out) {
-    FFB_REQUIRE(npeers <= 8 && nouter <= 65535 && !o2.mod, FFB_EUNSUPPORTED, "peer-store pass: at most 8 ranks and 65535 slices");
-    p.use_peer = 1;
-    for (int q = 0; q < npeers; ++q) p.out_peer[q] = peer_out[q];
-  }
   // plain long strided passes: software-pipelined persistent kernel (fft_stream.cuh)
-  if (mode == C2C_COLS && !pro && !epi && !rmul && !peer_out && !o2.mod && in_ls == 1 && out_ls == 1 && stream_has(N) && N >= stream_min_n(sizeof(T))) {
+  if (mode == C2C_COLS && !pro && !epi && !rmul && !o2.mod && in_ls == 1 && out_ls == 1 && stream_has(N) && N >= stream_min_n(sizeof(T))) {
     const int Tn = N / 16;
     const bool seg_ok = (!in_seg.seg || in_seg.seg % Tn == 0) && (!out_seg.seg || out_seg.seg % Tn == 0);
     if (seg_ok) return stream_pass<T>(N, dir, in, out, in_es, in_os, out_es, out_os, nlines, nouter, scale, tw, st, in_seg, out_seg);
   }
   // plain strided passes: lean kernel variant with host-computed element offsets (needs segment lengths that are multiples of N/R)
+  long long lean_out_off[16] = {0};
   static int lean_env = -1;
   if (lean_env < 0) { const char* e = getenv("FFB_LEAN"); lean_env = e ? atoi(e) : 1; }
-  if (lean_env && mode == C2C_COLS && !pro && !epi && !rmul && !peer_out && !o2.mod && in_ls == 1 && out_ls == 1 && !g_pass_reverse) {
+  if (lean_env && mode == C2C_COLS && !pro && !epi && !rmul && !o2.mod && in_ls == 1 && out_ls == 1 && !g_pass_reverse) {
     const int R0 = pow2_points_per_thread(N), Tn = N / R0;
     if ((!in_seg.seg || in_seg.seg % Tn == 0) && (!out_seg.seg || out_seg.seg % Tn == 0)) {
       mode = C2C_COLS_LEAN;
       for (int m = 0; m < 16; ++m) {
         const long long i = (long long)m * Tn;
         p.in_off[m] = in_seg.seg ? (i % in_seg.seg) * in_es + (i / in_seg.seg) * in_seg.stride : i * in_es;
-        p.out_off[m] = out_seg.seg ? (i % out_seg.seg) * out_es + (i / out_seg.seg) * out_seg.stride : i * out_es;
+        lean_out_off[m] = out_seg.seg ? (i % out_seg.seg) * out_es + (i / out_seg.seg) * out_seg.stride : i * out_es;
       }
     }
   }
@@ -408,6 +402,10 @@ static int pow2_pass(int N, int mode, int dir, const void* in, void* out, long l
     const long long cnt = std::min<long long>(65535, nouter - o0);
     p.in = reinterpret_cast<const cx<T>*>(in) + o0 * in_os;
     p.out = reinterpret_cast<cx<T>*>(out) + o0 * out_os;
+    if (mode == C2C_COLS_LEAN) {
+      p.in_ts = p.W; p.out_ts = p.W;
+      for (int m = 0; m < 16; ++m) p.out_m[m] = reinterpret_cast<cx<T>*>(p.out) + lean_out_off[m];
+    }
     if (pro && pro->w) p.pro.w = pro->w + o0 * in_os;
     if (epi && epi->w) p.epi.w = epi->w + o0 * out_os;
     if (epi && epi->acc) p.epi.acc = epi->acc + o0 * out_os;
@@ -417,6 +415,35 @@ static int pow2_pass(int N, int mode, int dir, const void* in, void* out, long l
     if (rc) return rc;
   }
   return FFB_OK;
+}
+
+// Lean strided pass over tiles of W adjacent lines with explicit tile / outer / element strides, per-register input offsets
+// and per-register output base pointers (used by the slab decomposition: blocked receive layouts, stores into peer memory).
+template <typename T>
+static int lean_tile_pass(int N, int dir, int W, const cx<T>* in, long long in_ts, long long in_os, long long in_es, const long long* in_off,
+                          cx<T>* const* out_m, long long out_ts, long long out_os, long long out_es, long long nlines, long long nouter, T scale,
+                          const cx<T>* tw, cudaStream_t st) {
+  Pow2Params<T> p;
+  const int R = pow2_points_per_thread(N), Tn = N / R;
+  FFB_REQUIRE(R == 16 && Tn * W <= pow2_max_threads(sizeof(T)) && nouter <= 65535, FFB_EUNSUPPORTED,
+              "blocked strided pass: line length %d with %d-wide tiles is outside the kernel range", N, W);
+  p.pro.on = 0; p.epi.on = 0; p.rmul = nullptr; p.reverse = 0; p.keep_out = 0;
+  p.in = in; p.out = nullptr;
+  p.in_es = in_es; p.in_ls = 1; p.in_os = in_os; p.out_es = out_es; p.out_ls = 1; p.out_os = out_os;
+  p.in_os2 = p.out_os2 = 0; p.outer_mod = 1 << 30;
+  p.in_seg_mask = p.out_seg_mask = 0x7fffffff; p.in_seg_shift = p.out_seg_shift = 31; p.in_seg_stride = p.out_seg_stride = 0;
+  p.twN = nullptr; p.twN_mask = 0; p.twr = nullptr;
+  p.nlines = nlines; p.W = W; p.scale = scale; p.tw = tw;
+  p.in_ts = in_ts; p.out_ts = out_ts;
+  for (int m = 0; m < 16; ++m) { p.in_off[m] = in_off[m]; p.out_m[m] = out_m[m]; }
+  const int threads = Tn * W;
+  p.pf_ahead = threads >= pow2_max_threads(sizeof(T)) ? num_sms() : 0;
+  const size_t smem = pow2_smem_bytes<T>(N, W, C2C_COLS_LEAN);
+  const long long gx = (nlines + W - 1) / W;
+  char pname[64];
+  snprintf(pname, sizeof(pname), "fft_c2c_cols_%s_N%d", sizeof(T) == 8 ? "f64" : "f32", N);
+  ProfScope ps(pname, (double)nlines * (double)nouter * 2.0 * N * sizeof(cx<T>));
+  return call_pow2<T>(N, C2C_COLS_LEAN, dir, p, (int)gx, (int)nouter, threads, smem, st);
 }
 
 // strided (column) pass along dimension d: one register-resident pass, or the four-step pair A (in place allowed) + B
@@ -721,66 +748,111 @@ static int exec_dist(ffb_plan* pl, const void* in, void* out, int dir) {
   const T inv = (T)(1.0L / tot);
   SegStride seg; seg.seg = (int)nyl; seg.stride = blk;
   if (pl->p2p == 2) {
-    // ---- copy-engine exchange: each pass writes its z-chunk in destination-rank-major order (as for NCCL); the blocks are
-    //      pushed into the peers' receive buffers with cudaMemcpyAsync over NVLink (no SM, runs beside the next chunk's pass);
-    //      a one-element all-reduce on the communication stream tells the receiver that a chunk has landed everywhere ----
+    // ---- copy-engine exchange, pipelined over kx-chunks: the pass before the exchange writes chunk c (a range of kx) in
+    //      destination-rank-major order, cudaMemcpyAsync pushes the blocks into the peers' receive buffers over NVLink (no SM,
+    //      runs beside the passes of the neighbouring chunks), a one-element all-reduce on the communication stream tells the
+    //      receiver that chunk c has landed everywhere, and the pass after the exchange starts on chunk c right away ----
     const int cur = pl->p2p_cur;
     pl->p2p_cur ^= 1;
     cx<T>* mine = reinterpret_cast<cx<T>*>(pl->recv[cur]);
     const size_t esz = sizeof(cx<T>);
+    const int nc = (int)std::min<long long>(nch, nkr);
+    const long long kw = nkr / nc;                       // chunk width; the last chunk takes the remainder
+    cudaEvent_t landed[8];
+    auto k0_of = [&](int c) { return (long long)c * kw; };
+    auto kxc_of = [&](int c) { return c == nc - 1 ? nkr - (long long)c * kw : kw; };
     if (dir < 0) {
       if ((rc = pow2_pass<T>(N0, R2C_ROWS, -1, in, w0, 1, N0, 0, 1, nkr, 0, ny * nzl, 1, T(1), tb0->tw, tb0->twr, st))) return rc;
-      for (int c = 0; c < nch; ++c) {
-        if ((rc = pow2_pass<T>((int)ny, C2C_COLS, -1, w0 + c * zc * nkr * ny, w1 + c * sub, nkr, 1, nkr * ny, nkr, 1, nkr * nyl, nkr, zc, T(1), tb1->tw,
-                               nullptr, st, SegStride(), seg))) return rc;
-        if ((rc = dist_push_blocks(d, w1 + c * sub, pl->peers[cur], ((size_t)d->rank * blk + (size_t)c * sub) * esz, (size_t)sub * esz, (size_t)blk * esz, st))) return rc;
+      for (int c = 0; c < nc; ++c) {
+        const long long k0 = k0_of(c), kxc = kxc_of(c), blkc = kxc * nyl * nzl, off = k0 * nyl * nzl * P;
+        SegStride segc; segc.seg = (int)nyl; segc.stride = blkc;
+        // y on kx-chunk c: w0 (nkr, ny, nzl) -> w1 chunk [peer][kxc, nyl, nzl]
+        if ((rc = pow2_pass<T>((int)ny, C2C_COLS, -1, w0 + k0, w1 + off, nkr, 1, nkr * ny, kxc, 1, kxc * nyl, kxc, nzl, T(1), tb1->tw, nullptr, st,
+                               SegStride(), segc))) return rc;
+        if ((rc = dist_push_blocks(d, w1 + off, pl->peers[cur], ((size_t)off + (size_t)d->rank * blkc) * esz, (size_t)blkc * esz, (size_t)blkc * esz, st))) return rc;
+        if ((rc = dist_barrier(d, d->comm_stream))) return rc;
+        landed[c] = dist_next_event(d);   // ring of 64 events, at most 7 per chunk: no wrap-around before the waits below
+        FFB_CUDA(cudaEventRecord(landed[c], d->comm_stream));
       }
-      if ((rc = dist_barrier(d, d->comm_stream))) return rc;
-      cudaEvent_t e = dist_next_event(d);
-      FFB_CUDA(cudaEventRecord(e, d->comm_stream));
-      FFB_CUDA(cudaStreamWaitEvent(st, e, 0));
-      return pow2_pass<T>((int)nz, C2C_COLS, -1, mine, out, nkr * nyl, 1, 0, nkr * nyl, 1, 0, nkr * nyl, 1, T(1), tb2->tw, nullptr, st);
+      for (int c = 0; c < nc; ++c) {
+        const long long k0 = k0_of(c), kxc = kxc_of(c), off = k0 * nyl * nzl * P;
+        FFB_CUDA(cudaStreamWaitEvent(st, landed[c], 0));
+        // z on kx-chunk c: receive chunk [kxc, nyl, nz] -> out (nkr, nyl, nz)
+        if ((rc = pow2_pass<T>((int)nz, C2C_COLS, -1, mine + off, reinterpret_cast<cx<T>*>(out) + k0, kxc * nyl, 1, kxc, nkr * nyl, 1, nkr, kxc, nyl, T(1),
+                               tb2->tw, nullptr, st))) return rc;
+      }
+      return FFB_OK;
     }
-    if ((rc = pow2_pass<T>((int)nz, C2C_COLS, +1, in, w0, nkr * nyl, 1, 0, nkr * nyl, 1, 0, nkr * nyl, 1, T(1), tb2->tw, nullptr, st))) return rc;
-    cudaEvent_t landed[8];
-    for (int c = 0; c < nch; ++c) {
-      if ((rc = dist_push_blocks(d, w0 + c * sub, pl->peers[cur], ((size_t)d->rank * blk + (size_t)c * sub) * esz, (size_t)sub * esz, (size_t)blk * esz,
-                                 c == 0 ? st : nullptr))) return rc;
+    for (int c = 0; c < nc; ++c) {
+      const long long k0 = k0_of(c), kxc = kxc_of(c), blkc = kxc * nyl * nzl, off = k0 * nyl * nzl * P;
+      // z on kx-chunk c: in (nkr, nyl, nz) -> w0 chunk [kxc, nyl, nz] (= [peer][kxc, nyl, nzl])
+      if ((rc = pow2_pass<T>((int)nz, C2C_COLS, +1, reinterpret_cast<const cx<T>*>(in) + k0, w0 + off, nkr * nyl, 1, nkr, kxc * nyl, 1, kxc, kxc, nyl, T(1),
+                             tb2->tw, nullptr, st))) return rc;
+      if ((rc = dist_push_blocks(d, w0 + off, pl->peers[cur], ((size_t)off + (size_t)d->rank * blkc) * esz, (size_t)blkc * esz, (size_t)blkc * esz, st))) return rc;
       if ((rc = dist_barrier(d, d->comm_stream))) return rc;
-      landed[c] = dist_next_event(d);   // ring of 64 events, at most 6 per chunk: no wrap-around before the wait below
+      landed[c] = dist_next_event(d);
       FFB_CUDA(cudaEventRecord(landed[c], d->comm_stream));
     }
-    for (int c = 0; c < nch; ++c) {
+    for (int c = 0; c < nc; ++c) {
+      const long long k0 = k0_of(c), kxc = kxc_of(c), blkc = kxc * nyl * nzl, off = k0 * nyl * nzl * P;
+      SegStride segc; segc.seg = (int)nyl; segc.stride = blkc;
       FFB_CUDA(cudaStreamWaitEvent(st, landed[c], 0));
-      if ((rc = pow2_pass<T>((int)ny, C2C_COLS, +1, mine + c * sub, w2 + c * zc * nkr * ny, nkr, 1, nkr * nyl, nkr, 1, nkr * ny, nkr, zc, T(1), tb1->tw, nullptr, st,
-                             seg, SegStride()))) return rc;
-      if ((rc = pow2_pass<T>(N0, C2R_ROWS, +1, w2 + c * zc * nkr * ny, reinterpret_cast<cx<T>*>(out) + c * zc * (long long)N0 * ny, 1, nkr, 0, 1, N0, 0,
-                             ny * zc, 1, inv, tb0->tw, tb0->twr, st))) return rc;
+      // y on kx-chunk c: receive chunk [sender][kxc, nyl, nzl] -> w2 (nkr, ny, nzl)
+      if ((rc = pow2_pass<T>((int)ny, C2C_COLS, +1, mine + off, w2 + k0, kxc, 1, kxc * nyl, nkr, 1, nkr * ny, kxc, nzl, T(1), tb1->tw, nullptr, st,
+                             segc, SegStride()))) return rc;
     }
-    return FFB_OK;
+    return pow2_pass<T>(N0, C2R_ROWS, +1, w2, out, 1, nkr, 0, 1, N0, 0, ny * nzl, 1, inv, tb0->tw, tb0->twr, st);
   }
-  if (pl->p2p) {
-    // ---- fused pass + collective: the pass before the exchange stores directly into the peers' receive buffers (NVLink),
-    //      one stream-ordered barrier replaces the all-to-all; receive buffers are double-buffered across transforms ----
+  if (pl->p2p == 1) {
+    // ---- fused pass + collective: the pass before the exchange stores straight into the peers' receive buffers (NVLink),
+    //      one stream-ordered barrier replaces the all-to-all; receive buffers are double-buffered across transforms.
+    //      The receive layout is blocked, [kx block of B][..][..][B] with B*sizeof(complex) = 64 bytes, chosen so that the four
+    //      consecutive line elements a warp stores together are contiguous in the peer's memory (256-byte NVLink writes instead
+    //      of 64-byte ones: 710 vs 310 GB/s measured) while the pass after the exchange still reads 64-byte rows. ----
     const int cur = pl->p2p_cur;
     pl->p2p_cur ^= 1;
     cx<T>* mine = reinterpret_cast<cx<T>*>(pl->recv[cur]);
-    cx<T>* dests[8];
-    for (int q = 0; q < P; ++q) dests[q] = reinterpret_cast<cx<T>*>(pl->peers[cur][q]) + (long long)d->rank * blk;
+    constexpr int B = 64 / (int)sizeof(cx<T>);
+    const long long nkt = (nkr + B - 1) / B;           // kx blocks (the last one is ragged)
+    const int Tny = (int)ny / 16, Tnz = (int)nz / 16;   // line elements per register step
+    long long off[16];
+    cx<T>* dst[16];
     if (dir < 0) {
       if ((rc = pow2_pass<T>(N0, R2C_ROWS, -1, in, w0, 1, N0, 0, 1, nkr, 0, ny * nzl, 1, T(1), tb0->tw, tb0->twr, st))) return rc;
+      // y: w0 (nkr, ny, nzl) -> rank (y / nyl)'s buffer, layout [kt][z][yl][B] with z = rank*nzl + zl
+      for (int m = 0; m < 16; ++m) {
+        const long long y = (long long)m * Tny;
+        off[m] = y * nkr;
+        dst[m] = reinterpret_cast<cx<T>*>(pl->peers[cur][y / nyl]) + ((long long)d->rank * nzl * nyl + (y % nyl)) * B;
+      }
       { ProfScope ps("fft_y_pass_peer_store", 0);
-      if ((rc = pow2_pass<T>((int)ny, C2C_COLS, -1, w0, mine, nkr, 1, nkr * ny, nkr, 1, nkr * nyl, nkr, nzl, T(1), tb1->tw, nullptr, st, SegStride(), seg,
-                             Outer2(), nullptr, 0, nullptr, nullptr, nullptr, dests, P))) return rc; }
+      if ((rc = lean_tile_pass<T>((int)ny, -1, B, w0, B, nkr * ny, nkr, off, dst, nz * nyl * B, nyl * B, B, nkr, nzl, T(1), tb1->tw, st))) return rc; }
       if ((rc = dist_barrier(d, st))) return rc;
-      return pow2_pass<T>((int)nz, C2C_COLS, -1, mine, out, nkr * nyl, 1, 0, nkr * nyl, 1, 0, nkr * nyl, 1, T(1), tb2->tw, nullptr, st);
+      // z: own buffer [kt][z][yl][B] -> out (nkr, nyl, nz)
+      for (int m = 0; m < 16; ++m) {
+        const long long z = (long long)m * Tnz;
+        off[m] = z * nyl * B;
+        dst[m] = reinterpret_cast<cx<T>*>(out) + z * nkr * nyl;
+      }
+      return lean_tile_pass<T>((int)nz, -1, B, mine, nz * nyl * B, B, nyl * B, off, dst, B, nkr, nkr * nyl, nkr, nyl, T(1), tb2->tw, st);
     }
-    SegStride segz; segz.seg = (int)nzl; segz.stride = blk;
+    // z: in (nkr, nyl, nz) -> rank (z / nzl)'s buffer, layout [kt][y][zl][B] with y = rank*nyl + yl
+    for (int m = 0; m < 16; ++m) {
+      const long long z = (long long)m * Tnz;
+      off[m] = z * nkr * nyl;
+      dst[m] = reinterpret_cast<cx<T>*>(pl->peers[cur][z / nzl]) + ((long long)d->rank * nyl * nzl + (z % nzl)) * B;
+    }
     { ProfScope ps("fft_z_pass_peer_store", 0);
-    if ((rc = pow2_pass<T>((int)nz, C2C_COLS, +1, in, mine, nkr * nyl, 1, 0, nkr * nyl, 1, 0, nkr * nyl, 1, T(1), tb2->tw, nullptr, st, SegStride(), segz,
-                           Outer2(), nullptr, 0, nullptr, nullptr, nullptr, dests, P))) return rc; }
+    if ((rc = lean_tile_pass<T>((int)nz, +1, B, reinterpret_cast<const cx<T>*>(in), B, nkr, nkr * nyl, off, dst, ny * nzl * B, nzl * B, B, nkr, nyl, T(1), tb2->tw, st))) return rc; }
     if ((rc = dist_barrier(d, st))) return rc;
-    if ((rc = pow2_pass<T>((int)ny, C2C_COLS, +1, mine, w2, nkr, 1, nkr * nyl, nkr, 1, nkr * ny, nkr, nzl, T(1), tb1->tw, nullptr, st, seg, SegStride()))) return rc;
+    // y: own buffer [kt][y][zl][B] -> w2 (nkr, ny, nzl)
+    for (int m = 0; m < 16; ++m) {
+      const long long y = (long long)m * Tny;
+      off[m] = y * nzl * B;
+      dst[m] = w2 + y * nkr;
+    }
+    if ((rc = lean_tile_pass<T>((int)ny, +1, B, mine, ny * nzl * B, B, nzl * B, off, dst, B, nkr * ny, nkr, nkr, nzl, T(1), tb1->tw, st))) return rc;
+    (void)nkt;
     return pow2_pass<T>(N0, C2R_ROWS, +1, w2, out, 1, nkr, 0, 1, N0, 0, ny * nzl, 1, inv, tb0->tw, tb0->twr, st);
   }
   if (dir < 0) {
@@ -848,7 +920,7 @@ int ffb_plan_create(ffb_plan** out, int ndim, const int64_t* n, int dtype, int k
   auto* pl = new ffb_plan();
   pl->ndim = ndim; pl->dtype = dtype; pl->kind = kind; pl->nbatch = nbatch; pl->flags = flags;
   pl->dist = nullptr; pl->nyl = pl->nzl = 0; pl->nchunks = 1;
-  pl->recv[0] = pl->recv[1] = nullptr; pl->p2p = 0; pl->p2p_cur = 0;
+  pl->recv[0] = pl->recv[1] = nullptr; pl->p2p = 0; pl->p2p_cur = 0; pl->recv_bytes = 0;
   for (int b = 0; b < 2; ++b) for (int q = 0; q < 8; ++q) pl->peers[b][q] = nullptr;
   for (int d = 0; d < 3; ++d) { pl->n[d] = d < ndim ? n[d] : 1; pl->nc[d] = pl->n[d]; pl->tables[d] = nullptr; pl->ws[d] = nullptr; }
   if (kind == FFB_R2C) pl->nc[0] = pl->n[0] / 2 + 1;
@@ -884,12 +956,36 @@ int ffb_plan_create_dist(ffb_plan** out, int ndim, const int64_t* n, int dtype, 
   return FFB_OK;
 }
 
+// Receive buffers of the peer-memory exchanges.  Both halves live in ONE allocation that is never returned to the driver
+// while the process lives: peers keep it mapped (CUDA IPC), so a later plan of the same size reuses it (pool below).
+namespace {
+struct RecvSlab { void* p; size_t bytes; bool in_use; };
+std::vector<RecvSlab> g_recv_pool;
+}  // namespace
+
 int ffb_plan_dist_recv_buffers(ffb_plan* pl, void** buf0, void** buf1, size_t* bytes_each) {
   FFB_REQUIRE(pl && pl->dist && buf0 && buf1, FFB_EINVAL, "needs a slab-decomposed plan");
-  for (int b = 0; b < 2; ++b)
-    if (!pl->recv[b]) { int rc = ffb_malloc(&pl->recv[b], pl->ws_bytes); if (rc) return rc; }
+  if (!pl->recv[0]) {
+    // room for the kx-padded blocked layout of the peer-store exchange (kx rounded up to whole 64-byte blocks)
+    const size_t esz = 2 * dtype_size(pl->dtype);
+    const size_t nkrp = ((size_t)pl->nc[0] + 7) / 8 * 8;
+    size_t each = nkrp * (size_t)pl->n[1] * (size_t)pl->nzl * esz;
+    each = (each + (2u << 20) - 1) / (2u << 20) * (2u << 20);   // whole 2 MiB pages: the allocation is not shared with other buffers
+    if (each < (2u << 20)) each = 2u << 20;
+    void* slab = nullptr;
+    for (auto& r : g_recv_pool)
+      if (!r.in_use && r.bytes == 2 * each) { r.in_use = true; slab = r.p; break; }
+    if (!slab) {
+      int rc = ffb_malloc(&slab, 2 * each);
+      if (rc) return rc;
+      g_recv_pool.push_back({slab, 2 * each, true});
+    }
+    pl->recv[0] = slab;
+    pl->recv[1] = reinterpret_cast<char*>(slab) + each;
+    pl->recv_bytes = each;
+  }
   *buf0 = pl->recv[0]; *buf1 = pl->recv[1];
-  if (bytes_each) *bytes_each = pl->ws_bytes;
+  if (bytes_each) *bytes_each = pl->recv_bytes;
   return FFB_OK;
 }
 
@@ -905,8 +1001,6 @@ int ffb_plan_dist_set_peers(ffb_plan* pl, void* const* peers0, void* const* peer
   }
   FFB_REQUIRE(pl->peers[0][pl->dist->rank] == pl->recv[0] && pl->peers[1][pl->dist->rank] == pl->recv[1], FFB_EINVAL,
               "the entry of the own rank must be the local receive buffer");
-  pl->p2p = 1;
-  pl->desc += "peer-store-exchange ";
   return FFB_OK;
 }
 
@@ -915,6 +1009,13 @@ int ffb_plan_dist_set_exchange(ffb_plan* pl, int mode) {
   FFB_REQUIRE(mode == FFB_EXCHANGE_NCCL || mode == FFB_EXCHANGE_PEER_STORE || mode == FFB_EXCHANGE_COPY_ENGINE, FFB_EINVAL, "bad exchange mode %d", mode);
   FFB_REQUIRE(mode == FFB_EXCHANGE_NCCL || pl->peers[0][0], FFB_EINVAL, "call ffb_plan_dist_set_peers first");
   FFB_REQUIRE(pl->nchunks <= 8, FFB_EUNSUPPORTED, "too many chunks");
+  if (mode == FFB_EXCHANGE_PEER_STORE) {
+    // the blocked passes use 64-byte wide tiles: line length * tile width must fit one CTA
+    const int maxn = 16 * pow2_max_threads(dtype_size(pl->dtype)) / (64 / (2 * (int)dtype_size(pl->dtype)));
+    FFB_REQUIRE(pl->n[1] >= 16 && pl->n[2] >= 16 && pl->n[1] <= maxn && pl->n[2] <= maxn, FFB_EUNSUPPORTED,
+                "peer-store exchange needs 16 <= ny, nz <= %d for this precision", maxn);
+    FFB_REQUIRE(pl->nyl % (pl->n[1] / 16) == 0 && pl->nzl % (pl->n[2] / 16) == 0, FFB_EUNSUPPORTED, "peer-store exchange needs at most 16 ranks");
+  }
   pl->p2p = mode;
   static const char* names[3] = {"exchange=nccl ", "exchange=peer-store ", "exchange=copy-engine "};
   pl->desc += names[mode];
@@ -925,7 +1026,8 @@ int ffb_plan_destroy(ffb_plan* pl) {
   if (!pl) return FFB_OK;
   if (pl->dtype == FFB_F64) free_tables<double>(pl); else free_tables<float>(pl);
   for (int i = 0; i < 3; ++i) cudaFree(pl->ws[i]);
-  cudaFree(pl->recv[0]); cudaFree(pl->recv[1]);
+  for (auto& r : g_recv_pool)
+    if (r.p == pl->recv[0]) r.in_use = false;   // stays allocated: peers may still have it mapped
   delete pl;
   return FFB_OK;
 }

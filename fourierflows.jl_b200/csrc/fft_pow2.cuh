@@ -37,10 +37,6 @@ struct Pow2Params {
   // so a pass can read / write destination-rank-major blocks without a pack kernel.  Unsegmented: mask = ~0, shift = 31.
   int in_seg_mask, in_seg_shift, out_seg_mask, out_seg_shift;
   long long in_seg_stride, out_seg_stride;
-  // Fused pass + collective (slab decomposition): when use_peer != 0 output segment s = (i >> out_seg_shift) is stored
-  // straight into rank s's receive buffer (peer memory mapped through CUDA IPC, NVLink stores) instead of out + s*seg_stride.
-  cx<T>* out_peer[8];
-  int use_peer;
   // two-level outer index: blockIdx.y = o -> (o % outer_mod)*os + (o / outer_mod)*os2   (outer_mod = 1<<30 when unused)
   int outer_mod;
   long long in_os2, out_os2;
@@ -70,7 +66,12 @@ struct Pow2Params {
   T scale;                           // applied to the output when != 1 (inverse normalisation)
   const cx<T>* tw;                   // base twiddles, forward sign: for each pass with Ns > 1, exp(-2 pi i a/(Ns r)), a < Ns
   const cx<T>* twr;                  // exp(-i*pi*k/N), k < N, for the r2c / c2r split step
-  long long in_off[16], out_off[16]; // C2C_COLS_LEAN: offset of register m's element (segmented strides folded in by the host)
+  // C2C_COLS_LEAN: tile bx starts at bx*ts, register m's element lives at in + in_off[m] / out_m[m] (segmented strides and,
+  // for the fused pass + collective of the slab decomposition, the destination rank's receive buffer -- peer memory mapped
+  // through CUDA IPC, NVLink stores -- are folded into these by the host)
+  long long in_ts, out_ts;
+  long long in_off[16];
+  cx<T>* out_m[16];
 };
 
 template <int... Rs> struct radix_product;
@@ -332,16 +333,16 @@ __global__ void __launch_bounds__(MAXT, MINB) fft_pow2_kernel(const Pow2Params<T
       });
     });
   } else if constexpr (LEAN) {
-    const cx<T>* in = reinterpret_cast<const cx<T>*>(p.in) + (long long)by * p.in_os + line + (long long)t * p.in_es;
+    const cx<T>* in = reinterpret_cast<const cx<T>*>(p.in) + (long long)by * p.in_os + (long long)bx * p.in_ts + w + (long long)t * p.in_es;
 #pragma unroll
     for (int m = 0; m < R; ++m) v[m] = active ? ldc(in + p.in_off[m]) : mk<T>(0, 0);
     // one CTA per SM runs its load / butterfly / store phases back to back: pull the tile that starts `pf_ahead` CTAs later
     // into L2 while this one computes, so that its load phase is an L2 hit
     if (p.pf_ahead > 0) {
       const long long lt = (long long)by * gridDim.x + bx + p.pf_ahead;
-      const long long pby = lt / gridDim.x, pline = (lt % gridDim.x) * W + w;
-      if (pby < gridDim.y && pline < p.nlines) {
-        const cx<T>* pin = reinterpret_cast<const cx<T>*>(p.in) + pby * p.in_os + pline + (long long)t * p.in_es;
+      const long long pby = lt / gridDim.x, pbx = lt % gridDim.x;
+      if (pby < gridDim.y && pbx * W + w < p.nlines) {
+        const cx<T>* pin = reinterpret_cast<const cx<T>*>(p.in) + pby * p.in_os + pbx * p.in_ts + w + (long long)t * p.in_es;
 #pragma unroll
         for (int m = 0; m < R; ++m) prefetch_l2(pin + p.in_off[m]);
       }
@@ -434,14 +435,14 @@ __global__ void __launch_bounds__(MAXT, MINB) fft_pow2_kernel(const Pow2Params<T
     }
   } else if constexpr (LEAN) {
     if (active) {
-      cx<T>* out = reinterpret_cast<cx<T>*>(p.out) + (long long)by * p.out_os + line + (long long)t * p.out_es;
+      const long long oo = (long long)by * p.out_os + (long long)bx * p.out_ts + w + (long long)t * p.out_es;
       const T sc = p.scale;
       if (sc != T(1)) {
 #pragma unroll
-        for (int m = 0; m < R; ++m) stk(out + p.out_off[m], sc * v[m], p.keep_out);
+        for (int m = 0; m < R; ++m) stk(p.out_m[m] + oo, sc * v[m], p.keep_out);
       } else {
 #pragma unroll
-        for (int m = 0; m < R; ++m) stk(out + p.out_off[m], v[m], p.keep_out);
+        for (int m = 0; m < R; ++m) stk(p.out_m[m] + oo, v[m], p.keep_out);
       }
     }
   } else {
@@ -461,17 +462,7 @@ __global__ void __launch_bounds__(MAXT, MINB) fft_pow2_kernel(const Pow2Params<T
       cx<T>* out = reinterpret_cast<cx<T>*>(p.out) + o_lo * p.out_os + o_hi * p.out_os2 + line * p.out_ls;
       const T sc = p.scale;
       auto off = [&](int i) { return (long long)(i & p.out_seg_mask) * p.out_es + (long long)(i >> p.out_seg_shift) * p.out_seg_stride; };
-      if (p.use_peer) {
-        const long long lo = o_lo * p.out_os + o_hi * p.out_os2 + line * p.out_ls;
-#pragma unroll
-        for (int m = 0; m < R; ++m) {
-          const int i = t + m * Tn;
-          cx<T>* dstp = p.out_peer[i >> p.out_seg_shift] + lo + (long long)(i & p.out_seg_mask) * p.out_es;
-          using V = typename vec2<T>::type;
-          V q; q.x = sc * v[m].x; q.y = sc * v[m].y;
-          *reinterpret_cast<V*>(dstp) = q;   // NVLink store (or local for the own segment)
-        }
-      } else if (p.epi.on) {
+      if (p.epi.on) {
         const int i0 = (int)(line % p.epi.n0);
         const long long io = p.epi.other_from_col == 1 ? line / p.epi.n0 : (p.epi.other_from_col == 2 ? (long long)o_lo : o_hi);
         const long long base = (out - reinterpret_cast<cx<T>*>(p.out));

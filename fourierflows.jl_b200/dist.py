@@ -91,18 +91,20 @@ class Dist:
 EXCHANGE = {"nccl": 0, "peer-store": 1, "copy-engine": 2}
 
 
-def enable_p2p(plan_handle, dist: "Dist", mode: str = "peer-store"):
+def enable_p2p(plan_handle, dist: "Dist", mode: str = "peer-store", T=None, shape=None):
     """Exchange the IPC handles of a plan's two receive buffers over torch.distributed, hand the mapped peer pointers to
     the plan (`ffb_plan_dist_set_peers`) and select the exchange (`ffb_plan_dist_set_exchange`):
-    "peer-store" = the pass before the exchange stores into the peers' buffers, "copy-engine" = chunked cudaMemcpyAsync pushes."""
+    "peer-store" = the pass before the exchange stores into the peers' buffers, "copy-engine" = chunked cudaMemcpyAsync pushes,
+    "auto" = measure and keep the fastest (needs T and the global shape).  Returns the exchange in use."""
     import torch.distributed as td
     b0, b1, nb = C.c_void_p(), C.c_void_p(), C.c_size_t()
     L.call("ffb_plan_dist_recv_buffers", plan_handle, C.byref(b0), C.byref(b1), C.byref(nb))
     h0, h1 = C.create_string_buffer(64), C.create_string_buffer(64)
-    L.call("ffb_dist_ipc_export", b0, h0)
-    L.call("ffb_dist_ipc_export", b1, h1)
+    o0, o1 = C.c_size_t(), C.c_size_t()
+    L.call("ffb_dist_ipc_export", b0, h0, C.byref(o0))
+    L.call("ffb_dist_ipc_export", b1, h1, C.byref(o1))
     gathered = [None] * dist.nranks
-    td.all_gather_object(gathered, (h0.raw, h1.raw))
+    td.all_gather_object(gathered, (h0.raw, o0.value, h1.raw, o1.value))
     P = dist.nranks
     p0, p1 = (C.c_void_p * P)(), (C.c_void_p * P)()
     for r in range(P):
@@ -110,12 +112,51 @@ def enable_p2p(plan_handle, dist: "Dist", mode: str = "peer-store"):
             p0[r], p1[r] = b0.value, b1.value
         else:
             q0, q1 = C.c_void_p(), C.c_void_p()
-            L.call("ffb_dist_ipc_open", C.create_string_buffer(gathered[r][0], 64), C.byref(q0))
-            L.call("ffb_dist_ipc_open", C.create_string_buffer(gathered[r][1], 64), C.byref(q1))
+            L.call("ffb_dist_ipc_open", C.create_string_buffer(gathered[r][0], 64), gathered[r][1], C.byref(q0))
+            L.call("ffb_dist_ipc_open", C.create_string_buffer(gathered[r][2], 64), gathered[r][3], C.byref(q1))
             p0[r], p1[r] = q0.value, q1.value
     L.call("ffb_plan_dist_set_peers", plan_handle, p0, p1)
-    L.call("ffb_plan_dist_set_exchange", plan_handle, EXCHANGE[mode])
     td.barrier()
+    if mode == "auto":
+        return autotune_exchange(plan_handle, dist, T, shape)
+    L.call("ffb_plan_dist_set_exchange", plan_handle, EXCHANGE[mode])
+    return mode
+
+
+def autotune_exchange(plan_handle, dist: "Dist", T, shape, reps: int = 2):
+    """Plan-time measurement (in the spirit of FFTW_MEASURE): time one forward + inverse transform of the plan's size with each
+    exchange the plan supports and keep the fastest.  Collective; every rank takes the same decision (max over ranks)."""
+    import time
+    import torch.distributed as td
+    P = dist.nranks
+    x = DevArray.zeros(T, (shape[0], shape[1], shape[2] // P))
+    xh = DevArray.zeros(cxtype(T), (shape[0] // 2 + 1, shape[1] // P, shape[2]))
+    results = {}
+    for mode in ("nccl", "copy-engine", "peer-store"):
+        try:
+            L.call("ffb_plan_dist_set_exchange", plan_handle, EXCHANGE[mode])
+        except L.FFBError:
+            continue   # not supported for this size
+        for timed in (False, True):
+            L.call("ffb_sync")
+            td.barrier()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                L.call("ffb_fft_forward", plan_handle, x.ptr, xh.ptr)
+                L.call("ffb_fft_inverse", plan_handle, xh.ptr, x.ptr)
+            L.call("ffb_sync")
+            dt = time.perf_counter() - t0
+        all_dt = [None] * P
+        td.all_gather_object(all_dt, dt)
+        results[mode] = max(all_dt) / reps
+    best = min(results, key=results.get)
+    L.call("ffb_plan_dist_set_exchange", plan_handle, EXCHANGE[best])
+    td.barrier()
+    AUTOTUNE_LOG.append({"shape": tuple(shape), "dtype": np.dtype(T).name, "ranks": P, "ms": {k: round(1e3 * v, 3) for k, v in results.items()}, "chosen": best})
+    return best
+
+
+AUTOTUNE_LOG = []
 
 
 class DistPlan:
@@ -142,7 +183,7 @@ class DistPlan:
         """Map every peer's receive buffers (CUDA IPC over NVLink) and exchange through them: "peer-store" (the pass before
         the exchange stores straight into them) or "copy-engine" (chunked cudaMemcpyAsync pushes beside the next chunk's pass).
         Collective call: every rank of the torch.distributed group must make it."""
-        enable_p2p(self._h, self.dist, mode)
+        self.exchange = enable_p2p(self._h, self.dist, mode, self.T, self.shape)
         return self
 
     def mul(self, out: DevArray, a: DevArray):

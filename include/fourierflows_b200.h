@@ -150,8 +150,10 @@ int ffb_plan_dist_set_peers(ffb_plan* plan, void* const* peers_buf0, void* const
  * transformed (no SM involved); a one-element all-reduce per chunk is the arrival barrier. */
 enum { FFB_EXCHANGE_NCCL = 0, FFB_EXCHANGE_PEER_STORE = 1, FFB_EXCHANGE_COPY_ENGINE = 2 };
 int ffb_plan_dist_set_exchange(ffb_plan* plan, int mode);
-int ffb_dist_ipc_export(void* dev_ptr, void* host_handle64);
-int ffb_dist_ipc_open(const void* host_handle64, void** dev_ptr);
+/* export: handle of the allocation that holds dev_ptr + offset of dev_ptr inside it; open: maps the allocation once per
+ * process (reference counted) and returns base + offset; close: drops one reference */
+int ffb_dist_ipc_export(void* dev_ptr, void* host_handle64, size_t* offset);
+int ffb_dist_ipc_open(const void* host_handle64, size_t offset, void** dev_ptr);
 int ffb_dist_ipc_close(void* dev_ptr);
 int ffb_dist_barrier(ffb_dist* dist);
 

@@ -29,10 +29,10 @@ def main():
         rng = np.random.default_rng(5)
         x = np.asfortranarray(rng.standard_normal(shape).astype(T))
         ref = fo.RfftPlan(shape, T) * x.astype(np.float64)
-        for nch in (0, 1, -1, -2):   # -1: fused pass + collective (peer stores over NVLink), -2: copy-engine pushes
+        for nch in (0, 1, -1, -2, -3):   # -1: fused pass + collective (peer stores over NVLink), -2: copy-engine pushes, -3: autotuned
             plan = ff.DistPlan(shape, T, comm, nchunks=max(nch, 0))
             if nch < 0:
-                plan.enable_p2p("peer-store" if nch == -1 else "copy-engine")
+                plan.enable_p2p({-1: "peer-store", -2: "copy-engine", -3: "auto"}[nch])
             xl = ff.DevArray.from_numpy(ff.physical_slab(x, P, rank))
             xh = plan * xl
             e1 = relerr(xh.to_numpy(), ff.spectral_slab(ref, P, rank))

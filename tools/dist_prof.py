@@ -26,8 +26,9 @@ def mx(v):
     return float(t.item())
 
 with torch.cuda.stream(stream):
-    for p2p in ("copy-engine", "peer-store", None):
-        for wenv in (None, "16"):
+    modes = sys.argv[4].split(",") if len(sys.argv) > 4 else ["copy-engine", "peer-store", "nccl"]
+    for p2p in [None if m == "nccl" else m for m in modes]:
+        for wenv in (None,):
             if wenv is None: os.environ.pop("FFB_W_COLS", None)
             else: os.environ["FFB_W_COLS"] = wenv
             plan = ff.DistPlan(shape, T, comm)
