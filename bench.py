@@ -94,7 +94,7 @@ class Burgers3D:
         self.shape, self.world = (nxy, nxy, nz_per_gpu * world), world
         self.name = (f"C5: 3-D Burgers-like ETDRK4 {self.shape} Float32 (ThreeDGrid, aliased_fraction=1/3, kappa={self.kappa}, dt={self.dt}), "
                      f"slab-decomposed over {world} GPUs, weak scaling in z ({nz_per_gpu} planes per GPU), random-phase IC")
-        self.parallelism = f"slab decomposition x{world}: physical z-slabs <-> spectral y-slabs, one NCCL all-to-all per 3-D transform"
+        self.parallelism = f"slab decomposition x{world}: physical z-slabs <-> spectral y-slabs, one exchange over NVLink per 3-D transform (see config.exchange)"
         self.replicas = 1
 
     def points(self):
@@ -142,13 +142,53 @@ def make_workload(args, world):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line).  NVML in a thread (10 ms
+    period, no process start-up inside the region); `nvidia-smi -lms` as fallback when pynvml is unusable."""
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
+        self.nvml, self.handle, self.stop_flag, self.thread = None, None, False, None
+        self.sm, self.pw, self.reasons, self.mx = [], [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:  # noqa: BLE001
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+                phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+                h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.nvml, self.handle = pynvml, h
+        except Exception:  # noqa: BLE001
+            self.nvml = None
+
+    def _sample(self):
+        n, h = self.nvml, self.handle
+        try:
+            self.sm.append(float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)))
+            self.pw.append(n.nvmlDeviceGetPowerUsage(h) / 1000.0)
+            fn = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+            mask = int(fn(h))
+            self.reasons |= {name for bit, name in self.BITS.items() if mask & bit}
+        except Exception:  # noqa: BLE001
+            pass
+
+    def _loop(self):
+        while not self.stop_flag:
+            self._sample()
+            time.sleep(0.01)
 
     def start(self):
+        if self.nvml is not None:
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -161,6 +201,12 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            if self.thread:
+                self.thread.join(timeout=1.0)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.mx, "reasons": sorted(self.reasons),
+                    "power_w_max": max(self.pw) if self.pw else None, "samples": len(self.sm), "source": "nvml"}
         if self.proc:
             self.proc.terminate()
         num = lambda s: s.replace(".", "").isdigit()
@@ -170,7 +216,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for r in self.rows if len(r) >= 8 for i in range(4) if r[4 + i].lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "source": "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------ CPU arms
@@ -278,7 +324,8 @@ def run_gpu(args):
         kernels = [{"name": r["name"], "share": round(r["ms"] / tot_ms, 4), "us_per_launch": round(1e3 * r["ms"] / r["launches"], 2),
                     "gbs": round(r["bytes"] / r["ms"] / 1e6, 1), "frac": round(r["bytes"] / r["ms"] / 1e6 / peak, 4)} for r in rep]
         roofline = {"bound": "hbm", "kernel": top["name"], "achieved": top["bytes"] / top["ms"] / 1e6, "peak": peak, "unit": "GB/s",
-                    "frac": top["bytes"] / top["ms"] / 1e6 / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": top["bytes"] / top["ms"] / 1e6 / peak, "traffic": ncu_traffic(top["name"])[0], "traffic_source": ncu_traffic(top["name"])[1],
+                    "peak_source": peak_src,
                     "share_of_step": top["ms"] / tot_ms, "algorithmic_bytes_per_launch": top["bytes"] / top["launches"]}
         # ---------------- FFT % of HBM peak: standalone r2c / c2r at the same size ----------------
         plan = wl.fft_plan(ff, L, comm)
@@ -351,6 +398,22 @@ def run_gpu(args):
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
+
+
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed `ncu --set full` summaries
+    (profiles/r01_ncu_full_*_kernels.csv; mean over the captured launches).  (None, None) when the kernel was not captured."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    for fn in ("r01_ncu_full_step_kernels.csv", "r01_ncu_full_fft3d_f32_kernels.csv"):
+        try:
+            lines = [l for l in open(os.path.join(here, "profiles", fn)) if not l.startswith("#")]
+        except OSError:
+            continue
+        cols = lines[0].strip().split(",")
+        vals = [float(l.split(",")[cols.index("traffic_MB")]) for l in lines[1:] if l.split(",")[0] in (kernel + "_fwd", kernel + "_inv", kernel)]
+        if vals:
+            return sum(vals) / len(vals) * 1e6, f"profiles/{fn} ({len(vals)} launches)"
+    return None, None
 
 
 def exchange_desc(prob, world, wl):

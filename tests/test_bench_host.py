@@ -1,0 +1,59 @@
+"""Host-side pieces of bench.py that run without a GPU: workload definitions, the byte model of the step roofline, the
+ncu traffic lookup from the committed summaries, the clock sampler's no-device fallback and the reference arm's JSON line."""
+import importlib.util
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def bench():
+    spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(ROOT, "bench.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def test_ncu_traffic_lookup(bench):
+    tr, src = bench.ncu_traffic("fft_c2c_cols_tw_f64_N64")
+    assert src and "profiles/" in src
+    # per-launch DRAM traffic of the twiddled four-step sub-pass at 8192^2 Float64: at least the algorithmic 2 x 537 MB
+    assert 1.0e9 < tr < 1.5e9
+    tr32, _ = bench.ncu_traffic("fft_c2c_cols_f32_N2048")
+    assert abs(tr32 - 2 * 1025 * 2048 * 256 * 8) / tr32 < 0.02      # traffic == algorithmic bytes: one HBM round trip, no re-reads
+    assert bench.ncu_traffic("no_such_kernel") == (None, None)
+
+
+def test_clock_sampler_without_device_reports_no_samples(bench):
+    s = bench.ClockSampler(0)
+    s.start()
+    out = s.stop()
+    assert set(out) >= {"sm_mhz", "sm_max_mhz", "reasons", "samples"}
+    assert out["samples"] == 0 or out["sm_mhz"] is not None
+
+
+def test_workloads_match_baseline_configs(bench):
+    class A:
+        workload, n, n3, nz_per_gpu = "auto", 8192, 2048, 256     # bench.py's defaults
+    base = json.load(open(os.path.join(ROOT, "BASELINE.json")))
+    text = json.dumps(base)
+    assert "8192" in text and "2048" in text
+    w1 = bench.make_workload(A(), 1)
+    assert tuple(w1.shape) == (8192, 8192) and np.dtype(w1.T) == np.float64
+    w8 = bench.make_workload(A(), 8)
+    assert tuple(w8.shape) == (2048, 2048, 2048) and np.dtype(w8.T) == np.float32
+    w2 = bench.make_workload(A(), 2)
+    assert tuple(w2.shape) == (2048, 2048, 512)      # weak scaling: 256 z-planes per GPU
+
+
+def test_reference_arm_other_ranks_exit_quietly():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, env=env, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip() == ""
