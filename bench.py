@@ -245,7 +245,7 @@ def run_reference(args):
     if rank != 0:
         return
     wl = make_workload(args, args.gpus)
-    n_sample = min(wl.shape[0], 2048) if len(wl.shape) == 2 else min(wl.shape[0], 128)
+    n_sample = min(wl.shape[0], 2048) if len(wl.shape) == 2 else min(wl.shape[0], 256)
     cb = cpu_arm(wl, n_sample, args.steps, max(1, args.warmup))
     line = {"impl": "reference", "metric": "ETDRK4 Gpt*steps/s (grid points x steps per second / 1e9)", "value": cb["value"], "unit": "Gpt*steps/s",
             "steps_per_s": cb["steps_per_s"], "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,

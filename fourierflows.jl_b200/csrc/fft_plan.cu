@@ -6,6 +6,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <mutex>
 #include <vector>
 #include "fft_generic.cuh"
 #include "fft_pow2.cuh"
@@ -961,6 +962,7 @@ int ffb_plan_create_dist(ffb_plan** out, int ndim, const int64_t* n, int dtype, 
 namespace {
 struct RecvSlab { void* p; size_t bytes; bool in_use; };
 std::vector<RecvSlab> g_recv_pool;
+std::mutex g_recv_mu;   // plans may be created / destroyed from different host threads (Julia finalizers)
 }  // namespace
 
 int ffb_plan_dist_recv_buffers(ffb_plan* pl, void** buf0, void** buf1, size_t* bytes_each) {
@@ -973,6 +975,7 @@ int ffb_plan_dist_recv_buffers(ffb_plan* pl, void** buf0, void** buf1, size_t* b
     each = (each + (2u << 20) - 1) / (2u << 20) * (2u << 20);   // whole 2 MiB pages: the allocation is not shared with other buffers
     if (each < (2u << 20)) each = 2u << 20;
     void* slab = nullptr;
+    std::lock_guard<std::mutex> lk(g_recv_mu);
     for (auto& r : g_recv_pool)
       if (!r.in_use && r.bytes == 2 * each) { r.in_use = true; slab = r.p; break; }
     if (!slab) {
@@ -1018,6 +1021,8 @@ int ffb_plan_dist_set_exchange(ffb_plan* pl, int mode) {
   }
   pl->p2p = mode;
   static const char* names[3] = {"exchange=nccl ", "exchange=peer-store ", "exchange=copy-engine "};
+  const size_t prev = pl->desc.find("exchange=");
+  if (prev != std::string::npos) pl->desc.erase(prev);   // the description names the exchange in use, not the history
   pl->desc += names[mode];
   return FFB_OK;
 }
@@ -1026,8 +1031,11 @@ int ffb_plan_destroy(ffb_plan* pl) {
   if (!pl) return FFB_OK;
   if (pl->dtype == FFB_F64) free_tables<double>(pl); else free_tables<float>(pl);
   for (int i = 0; i < 3; ++i) cudaFree(pl->ws[i]);
-  for (auto& r : g_recv_pool)
-    if (r.p == pl->recv[0]) r.in_use = false;   // stays allocated: peers may still have it mapped
+  if (pl->recv[0]) {
+    std::lock_guard<std::mutex> lk(g_recv_mu);
+    for (auto& r : g_recv_pool)
+      if (r.p == pl->recv[0]) r.in_use = false;   // stays allocated: peers may still have it mapped
+  }
   delete pl;
   return FFB_OK;
 }

@@ -116,6 +116,9 @@ def enable_p2p(plan_handle, dist: "Dist", mode: str = "peer-store", T=None, shap
             L.call("ffb_dist_ipc_open", C.create_string_buffer(gathered[r][2], 64), gathered[r][3], C.byref(q1))
             p0[r], p1[r] = q0.value, q1.value
     L.call("ffb_plan_dist_set_peers", plan_handle, p0, p1)
+    # receive buffers are pooled per process and may have served an earlier plan: every rank drains its own stream, then all
+    # ranks meet, so no peer can store into a buffer its owner is still reading for the previous plan
+    L.call("ffb_sync")
     td.barrier()
     if mode == "auto":
         return autotune_exchange(plan_handle, dist, T, shape)

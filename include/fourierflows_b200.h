@@ -144,6 +144,9 @@ int ffb_plan_create_dist(ffb_plan** plan, int ndim, const int64_t* n, int dtype,
  * them, every rank opens its peers' handles and hands the mapped pointers (own rank: its local buffer) to the plan. */
 int ffb_plan_dist_recv_buffers(ffb_plan* plan, void** buf0, void** buf1, size_t* bytes_each);
 int ffb_plan_dist_set_peers(ffb_plan* plan, void* const* peers_buf0, void* const* peers_buf1);   /* arrays of nranks pointers */
+/* Receive buffers are pooled per process (peers keep them mapped) and may have served an earlier plan: between
+ * ffb_plan_dist_set_peers and the first transform every rank must drain its stream (ffb_sync) and all ranks must meet in a
+ * host barrier of the launcher. */
 /* Exchange used by a slab-decomposed plan.  NCCL: chunked grouped send/recv (default, needs no peer mapping).
  * PEER_STORE: the fused pass described above (selected by ffb_plan_dist_set_peers).  COPY_ENGINE: the passes write
  * destination-major chunks and cudaMemcpyAsync pushes them into the peers' receive buffers while the next chunk is being
