@@ -1,6 +1,7 @@
 """Host-side logic of the slab decomposition with world_size = 2 over gloo (no GPU): rendezvous + NCCL unique-id
 broadcast plumbing, slab partitioning, and the exchange layout of csrc/fft_plan.cu::exec_dist restated in NumPy
-(y-pass output written destination-rank-major [peer][kx, y_local, z_local]; blocks received into (nkr, ny/P, nz))."""
+(y-pass output written destination-rank-major [peer][kx, y_local, z_local]; blocks received into (nkr, ny/P, nz)), and the
+blocked receive layouts of the fused pass + collective exchange (peer stores emulated by shipping (address, value) lists)."""
 import os
 import socket
 
@@ -58,6 +59,43 @@ def _worker(rank, world, port, q):
         out = sfft.fft(recv, axis=2)
         err = np.linalg.norm(out - ff.spectral_slab(ref, P, rank)) / np.linalg.norm(ref)
         assert err < 1e-13, err
+        # 2b. the fused pass + collective (FFB_EXCHANGE_PEER_STORE): the y-pass stores into the destination rank's receive buffer
+        #     with the blocked layout [kx block][z][y_local][B] of exec_dist (B complex = 64 bytes; ragged last kx block), the
+        #     z-pass reads that layout; inverse: [kx block][y][z_local][B].  Peer stores are emulated by shipping (address, value).
+        B = 4
+        nkt = (nkr + B - 1) // B
+        kx, yy, zl = np.meshgrid(np.arange(nkr), np.arange(ny), np.arange(nzl), indexing="ij")
+        addr = (((kx // B) * nz + (rank * nzl + zl)) * nyl + (yy % nyl)) * B + kx % B
+        stores = [(addr[yy // nyl == q], a[yy // nyl == q]) for q in range(P)]
+        inbox = [None] * P
+        for dst in range(P):
+            gathered = [None] * P
+            dist.all_gather_object(gathered, stores[dst])
+            if rank == dst:
+                inbox = gathered
+        flat = np.full(nkt * nz * nyl * B, np.nan + 0j)
+        for ad, val in inbox:
+            flat[ad] = val
+        kx2, yl2, z2 = np.meshgrid(np.arange(nkr), np.arange(nyl), np.arange(nz), indexing="ij")
+        recv_b = flat[(((kx2 // B) * nz + z2) * nyl + yl2) * B + kx2 % B]          # what the z-pass loads
+        assert np.array_equal(recv_b, recv)                                        # same data as the NCCL-layout exchange
+        spec_l = sfft.fft(recv_b, axis=2)
+        assert np.linalg.norm(spec_l - ff.spectral_slab(ref, P, rank)) / np.linalg.norm(ref) < 1e-13
+        # inverse: z-pass stores into rank (z // nzl) at [kx block][y = rank*nyl + y_local][z_local][B]
+        bz = sfft.ifft(spec_l, axis=2)
+        addr = (((kx2 // B) * ny + (rank * nyl + yl2)) * nzl + (z2 % nzl)) * B + kx2 % B
+        stores = [(addr[z2 // nzl == q], bz[z2 // nzl == q]) for q in range(P)]
+        for dst in range(P):
+            gathered = [None] * P
+            dist.all_gather_object(gathered, stores[dst])
+            if rank == dst:
+                inbox = gathered
+        flat = np.full(nkt * ny * nzl * B, np.nan + 0j)
+        for ad, val in inbox:
+            flat[ad] = val
+        by = flat[(((kx // B) * ny + yy) * nzl + zl) * B + kx % B]                 # what the inverse y-pass loads: (nkr, ny, nzl)
+        back = sfft.irfft(sfft.ifft(by, axis=1), n=nx, axis=0)
+        assert np.linalg.norm(back - xl) / np.linalg.norm(xl) < 1e-13
         # 3. alias ranges on the slab
         lal = ff.getaliasedwavenumbers(ny, ny // 2 + 1, 1 / 3)[0]
         loc = ff.local_alias_range(lal, ny, P, rank)
