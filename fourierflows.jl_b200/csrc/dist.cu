@@ -61,7 +61,7 @@ static int load_nccl() {
 
 cudaEvent_t dist_next_event(ffb_dist* d) {
   cudaEvent_t e = d->ev[d->ev_next];
-  d->ev_next = (d->ev_next + 1) % 64;
+  d->ev_next = (d->ev_next + 1) % ffb_dist::kEvents;
   return e;
 }
 

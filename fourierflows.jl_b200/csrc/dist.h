@@ -8,7 +8,8 @@ struct ffb_dist {
   void* comm;              // ncclComm_t
   int rank, nranks;
   cudaStream_t comm_stream;
-  cudaEvent_t ev[64];      // ring of events for compute <-> comm ordering
+  static constexpr int kEvents = 256;
+  cudaEvent_t ev[kEvents]; // ring of events for compute <-> comm ordering (one transform uses at most ~10 per chunk, <= 8 chunks)
   int ev_next;
   float* barrier_buf;      // device scratch of the barrier all-reduce
   cudaStream_t copy_streams[8];   // copy-engine exchange: peer copies are spread over these streams

@@ -772,7 +772,7 @@ static int exec_dist(ffb_plan* pl, const void* in, void* out, int dir) {
                                SegStride(), segc))) return rc;
         if ((rc = dist_push_blocks(d, w1 + off, pl->peers[cur], ((size_t)off + (size_t)d->rank * blkc) * esz, (size_t)blkc * esz, (size_t)blkc * esz, st))) return rc;
         if ((rc = dist_barrier(d, d->comm_stream))) return rc;
-        landed[c] = dist_next_event(d);   // ring of 64 events, at most 7 per chunk: no wrap-around before the waits below
+        landed[c] = dist_next_event(d);   // ring of 256 events, at most 10 per chunk and 8 chunks: no wrap-around before the waits below
         FFB_CUDA(cudaEventRecord(landed[c], d->comm_stream));
       }
       for (int c = 0; c < nc; ++c) {
