@@ -6,7 +6,9 @@
 #   B1  `zeros(::B200, T, dims)` / `device_array(::B200)`        (src/utils.jl:79-80, 329-332)
 #   B2  `plan_flows_rfft` / `plan_flows_fft`, `mul!`, `ldiv!`     (src/domains.jl:2-5; AbstractFFTs plan protocol)
 #   B3  one `stepforward!` method per stepper on B200 arrays      (src/timesteppers.jl:111-667)
-# `dealias!`, `makefilter`, `getetdcoeffs` get B200 methods as well.  No CUDA.jl, no KernelAbstractions, no CPU fallback.
+# `dealias!`, `makefilter`, `getetdcoeffs`, `parsevalsum(2)` get B200 methods as well; the closed elementwise vocabulary for user
+# `calcN!` (spectral_mul!, axpby!, mul_real!), the fused transforms, the C-driven problem and the multi-GPU plan are bound at
+# the end of the file.  No CUDA.jl, no KernelAbstractions, no CPU fallback.
 module FourierFlowsB200
 
 using FourierFlows
@@ -235,6 +237,80 @@ function spectral_mul!(out::B200Array, inp::B200Array, g; coef=1, px=0, py=0, pz
               out.ptr, inp.ptr, real(coef), imag(coef), (half ? g.kr : g.k).ptr, px, lp, py, mp, pz, w === nothing ? C_NULL : w.ptr, accumulate, dealias && kal !== nothing, d))
   return out
 end
+"`axpby!(out, a, x, b, y)` lowers `@. out = a*x + b*y` (y may be `nothing`): `L = @. -ν * grid.Krsq`, history copies, sums of fields"
+function axpby!(out::B200Array{T}, a::Real, x::B200Array{T}, b::Real=0.0, y::Union{B200Array{T},Nothing}=nothing) where T
+  check(ccall((:ffb_ew_axpby, lib), Cint, (Ptr{Cvoid}, Cdouble, Ptr{Cvoid}, Cdouble, Ptr{Cvoid}, Cint, Cint, Int64),
+              out.ptr, a, x.ptr, b, y === nothing ? C_NULL : y.ptr, T <: Complex, ffbtype(T), length(out)))
+  return out
+end
+"`mul_real!(out, x, y)` lowers the physical-space products `@. cx *= κ`, `@. u *= ζ` (src/diffusion.jl:138)"
+mul_real!(out::B200Array{T}, x::B200Array{T}, y::B200Array{T}) where T<:AbstractFloat =
+  (check(ccall((:ffb_ew_mul_real, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Int64), out.ptr, x.ptr, y.ptr, ffbtype(T), length(out))); out)
+
+# `parsevalsum2(uh, grid)` / `parsevalsum(uh, grid)` (src/utils.jl:113-183): device reduction, L/n^2 normalisation on the host
+function parsevalpartial(uh::B200Array, g, abs2::Bool)
+  r = Ref{Cdouble}(0.0)
+  d = Ref(desc(uh, g, nothing))
+  check(ccall((:ffb_parseval_sum, lib), Cint, (Ptr{Cdouble}, Ptr{Cvoid}, Cint, Cint, Ptr{FFBDesc}), r, uh.ptr, abs2, size(uh, 1) == g.nkr, d))
+  return r[]
+end
+FourierFlows.parsevalsum2(uh::B200Array, g::OneDGrid) = parsevalpartial(uh, g, true) * g.Lx / g.nx^2
+FourierFlows.parsevalsum2(uh::B200Array, g::TwoDGrid) = parsevalpartial(uh, g, true) * g.Lx * g.Ly / (g.nx^2 * g.ny^2)
+FourierFlows.parsevalsum(uh::B200Array, g::OneDGrid) = parsevalpartial(uh, g, false) * g.Lx / g.nx^2
+FourierFlows.parsevalsum(uh::B200Array, g::TwoDGrid) = parsevalpartial(uh, g, false) * g.Lx * g.Ly / (g.nx^2 * g.ny^2)
+
+# ---------------------------------------------------------------- fused transforms (north star: multiplies / dealias folded into the passes)
+struct FFBFuse
+  cr :: Cdouble; ci :: Cdouble
+  kx :: Ptr{Cvoid}; l :: Ptr{Cvoid}; m :: Ptr{Cvoid}; w :: Ptr{Cvoid}; acc :: Ptr{Cvoid}
+  ar :: Cdouble; ai :: Cdouble
+  akx :: Ptr{Cvoid}; al :: Ptr{Cvoid}; am :: Ptr{Cvoid}
+  dealias :: Cint; alias_lo :: NTuple{3,Int32}; alias_hi :: NTuple{3,Int32}
+  mul :: Ptr{Cvoid}
+end
+"`ldiv!(out, plan, ah, fuse)`: out = irfft(factor .* ah) [.* mul];  `mul!(outh, plan, a, fuse)`: outh = factor .* rfft(a) [+ g .* acc] [dealiased]"
+ldiv!(out::B200Array, p::B200Plan, ah::B200Array, f::FFBFuse) =
+  (check(ccall((:ffb_fft_inverse_ex, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{FFBFuse}), p.handle, ah.ptr, out.ptr, Ref(f))); out)
+mul!(out::B200Array, p::B200Plan, a::B200Array, f::FFBFuse) =
+  (check(ccall((:ffb_fft_forward_ex, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{FFBFuse}), p.handle, a.ptr, out.ptr, Ref(f))); out)
+
+# ---------------------------------------------------------------- C-driven loop (`ffb_step`): benchmarks, or user calcN! passed as @cfunction
+# typedef int (*ffb_calcN_fn)(void* N, const void* sol, double t, void* user)
+struct FFBProblemConfig
+  ndim :: Cint; n :: NTuple{3,Int64}; L :: NTuple{3,Cdouble}; dtype :: Cint; aliased_fraction :: Cdouble
+  stepper :: Cint; filtered :: Cint; filter_order :: Cdouble; filter_innerK :: Cdouble; filter_outerK :: Cdouble; filter_tol :: Cdouble
+  dt :: Cdouble; calcN :: Cint; callback :: Ptr{Cvoid}; user :: Ptr{Cvoid}; nu :: Cdouble; scalar_zero_L :: Cint
+  kappa :: Ptr{Cvoid}; coef_dtype :: Cint; fused :: Cint; dist :: Ptr{Cvoid}
+end
+mutable struct B200Problem; handle :: Ptr{Cvoid}; end
+function B200Problem(cfg::FFBProblemConfig)
+  h = Ref{Ptr{Cvoid}}(C_NULL)
+  check(ccall((:ffb_problem_create, lib), Cint, (Ptr{Ptr{Cvoid}}, Ptr{FFBProblemConfig}), h, Ref(cfg)))
+  p = B200Problem(h[])
+  finalizer(x -> ccall((:ffb_problem_destroy, lib), Cint, (Ptr{Cvoid},), x.handle), p)
+  return p
+end
+stepforward!(p::B200Problem, nsteps::Integer=1) = check(ccall((:ffb_step, lib), Cint, (Ptr{Cvoid}, Int64), p.handle, nsteps))   # src/timesteppers.jl:14-20
+FourierFlows.step_until!(p::B200Problem, stop_time) = check(ccall((:ffb_step_until, lib), Cint, (Ptr{Cvoid}, Cdouble), p.handle, stop_time))  # :734-760
+
+# ---------------------------------------------------------------- multi-GPU: one Julia process per GPU (MPI.jl moves the id and the IPC handles)
+# comm = MPI.COMM_WORLD; id = Vector{UInt8}(undef, 128); rank == 0 && ffb_dist_unique_id(id); MPI.Bcast!(id, 0, comm)
+# dist = ffb_dist_init(rank, nranks, id); plan = ffb_plan_create_dist(3, n, dtype, dist, 0)
+# peer memory: ffb_plan_dist_recv_buffers -> ffb_dist_ipc_export (handle + offset) -> MPI.Allgather -> ffb_dist_ipc_open ->
+#              ffb_plan_dist_set_peers -> ffb_sync + MPI.Barrier -> ffb_plan_dist_set_exchange(plan, 1 #= FFB_EXCHANGE_PEER_STORE =#)
+function distinit(rank::Integer, nranks::Integer, id::Vector{UInt8})
+  h = Ref{Ptr{Cvoid}}(C_NULL)
+  check(ccall((:ffb_dist_init, lib), Cint, (Ptr{Ptr{Cvoid}}, Cint, Cint, Ptr{UInt8}), h, rank, nranks, id))
+  return h[]
+end
+function makedistplan(::Type{T}, sz::NTuple{3,Int}, dist::Ptr{Cvoid}; nchunks=0) where T
+  h = Ref{Ptr{Cvoid}}(C_NULL)
+  check(ccall((:ffb_plan_create_dist, lib), Cint, (Ptr{Ptr{Cvoid}}, Cint, Ptr{Int64}, Cint, Ptr{Cvoid}, Cint), h, 3, Int64[sz...], ffbtype(T), dist, nchunks))
+  p = B200Plan{T,:r2c}(h[], sz)     # mul!/ldiv! act on the local slabs: (nx, ny, nz/P) <-> (nx/2+1, ny/P, nz)
+  finalizer(x -> ccall((:ffb_plan_destroy, lib), Cint, (Ptr{Cvoid},), x.handle), p)
+  return p
+end
+
 Base.Broadcast.BroadcastStyle(::Type{<:B200Array}) =
   error("generic broadcasting on B200Array is not supported: use spectral_mul!, axpby!, mul_real! (no CPU fallback)")
 
