@@ -21,9 +21,23 @@ def _ccalls():
             i += 1
         types = JL[m.end():i - 1].strip().rstrip(",")
         # split on top-level commas (Ptr{...} contains none, NTuple{3,Int32} would -- not used in signatures)
-        n = 0 if not types else len([t for t in re.split(r",(?![^{]*\})", types) if t.strip()])
-        out.append((m.group(1), m.group(2), n))
+        tl = [] if not types else [t.strip() for t in re.split(r",(?![^{]*\})", types) if t.strip()]
+        out.append((m.group(1), m.group(2), len(tl), tl))
     return out
+
+
+def _header_args(name):
+    m = re.search(r"\b" + name + r"\s*\(([^;]*?)\)\s*;", HDR, flags=re.S)
+    args = m.group(1).strip()
+    return [] if args in ("", "void") else [a.strip() for a in args.split(",")]
+
+
+def _compatible(jl, c):
+    if "*" in c:
+        return jl.startswith("Ptr{") or jl == "Cstring"
+    base = c.replace("const", "").split()
+    ctype = " ".join(base[:-1]) if len(base) > 1 else base[0]
+    return {"int": jl in ("Cint",), "int64_t": jl == "Int64", "double": jl == "Cdouble", "size_t": jl == "Csize_t"}.get(ctype, False)
 
 
 def _header_arity(name):
@@ -38,10 +52,12 @@ def test_every_ccall_targets_a_declared_symbol_with_the_right_arity():
     lib = ff._lib.load()
     calls = _ccalls()
     assert len(calls) >= 35
-    for name, ret, nargs in calls:
+    for name, ret, nargs, types in calls:
         assert hasattr(lib, name), f"{name} is not exported"
         assert _header_arity(name) == nargs, f"{name}: header takes {_header_arity(name)} arguments, the ccall passes {nargs}"
         assert ret in ("Cint", "Cstring"), (name, ret)
+        for k, (jl, c) in enumerate(zip(types, _header_args(name))):
+            assert _compatible(jl, c), f"{name} argument {k + 1}: Julia {jl} vs C `{c}`"
 
 
 @pytest.mark.parametrize("jl_struct,c_struct", [("FFBDesc", "ffb_desc"), ("FFBCoef", "ffb_coef"), ("FFBFuse", "ffb_fuse"),
