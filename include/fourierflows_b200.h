@@ -131,7 +131,8 @@ int ffb_fft_inverse_ex(ffb_plan* plan, const void* in, void* out, const ffb_fuse
  * capability named by BASELINE.json north_star.  One process per GPU; the caller (torch.distributed, MPI, ...) moves the
  * 128-byte NCCL unique id from rank 0 to the other ranks.  Physical arrays are split along z: rank r holds
  * (nx, ny, nz/P); spectral arrays along y: rank r holds (nx/2+1, ny/P, nz).  ffb_fft_forward / ffb_fft_inverse on a
- * distributed plan perform the local passes plus one NCCL all-to-all, overlapped chunk by chunk. */
+ * distributed plan perform the local passes plus one exchange (ffb_plan_dist_set_exchange; default: NCCL all-to-all,
+ * overlapped chunk by chunk). */
 int ffb_dist_unique_id(void* host_id128);
 int ffb_dist_init(ffb_dist** dist, int rank, int nranks, const void* host_id128);
 int ffb_dist_destroy(ffb_dist* dist);
@@ -148,9 +149,12 @@ int ffb_plan_dist_set_peers(ffb_plan* plan, void* const* peers_buf0, void* const
  * ffb_plan_dist_set_peers and the first transform every rank must drain its stream (ffb_sync) and all ranks must meet in a
  * host barrier of the launcher. */
 /* Exchange used by a slab-decomposed plan.  NCCL: chunked grouped send/recv (default, needs no peer mapping).
- * PEER_STORE: the fused pass described above (selected by ffb_plan_dist_set_peers).  COPY_ENGINE: the passes write
- * destination-major chunks and cudaMemcpyAsync pushes them into the peers' receive buffers while the next chunk is being
- * transformed (no SM involved); a one-element all-reduce per chunk is the arrival barrier. */
+ * PEER_STORE: the fused pass described above; the receive layout is blocked ([kx block][z][y_local][B] forward,
+ * [kx block][y][z_local][B] inverse, B complex = 64 bytes) so that a warp's stores are 256 contiguous bytes in the peer's
+ * memory; needs 16 <= ny, nz <= 2048 and at most 16 ranks (FFB_EUNSUPPORTED otherwise).  COPY_ENGINE: the passes write
+ * destination-major kx-chunks and cudaMemcpyAsync pushes them into the peers' receive buffers while the neighbouring
+ * chunks are being transformed (no SM involved); a one-element all-reduce per chunk is the arrival barrier.
+ * PEER_STORE and COPY_ENGINE need ffb_plan_dist_set_peers first. */
 enum { FFB_EXCHANGE_NCCL = 0, FFB_EXCHANGE_PEER_STORE = 1, FFB_EXCHANGE_COPY_ENGINE = 2 };
 int ffb_plan_dist_set_exchange(ffb_plan* plan, int mode);
 /* export: handle of the allocation that holds dev_ptr + offset of dev_ptr inside it; open: maps the allocation once per
