@@ -1,11 +1,11 @@
-"""fourierflows.jl_b200 -- B200-native drop-in for the pseudospectral time-stepping hot path of FourierFlows.jl.
+"""fourierflows_jl_b200 -- B200-native drop-in for the pseudospectral time-stepping hot path of FourierFlows.jl.
 
 Host-side mirror of the reference API (`OneDGrid/TwoDGrid/ThreeDGrid(dev; nx, Lx, ...)`, `Problem(eqn, stepper, dt, grid)`,
 `stepforward!`/`step_until!`, `dealias!`, `Diagnostic`, user `calcN!`/`L`) over the C ABI of `libfourierflows_b200.so`
 (include/fourierflows_b200.h).  Python + ctypes stands in for Julia + `ccall` (no Julia toolchain in this image; the
 Julia wrapper is `julia/FourierFlowsB200.jl`).  Julia's `f!` is spelled `f` here.
 
-The directory name contains a dot, so import it through the `fourierflows_jl_b200` alias module at the repo root.
+`fourierflows.jl_b200` at the repo root is a symlink to this directory (the name the task layout uses is not importable).
 """
 from . import _lib
 from ._lib import DomainError, FFBError, have_device, launch_count, prof_enable, prof_report

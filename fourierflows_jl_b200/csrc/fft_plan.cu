@@ -12,10 +12,6 @@
 #include "fft_pow2.cuh"
 #include "fft_pow2_dispatch.h"
 #include "dist.h"
-#include "fft_cluster.cuh"
-#include "fft_cluster_dispatch.h"
-#include "fft_stream.cuh"
-#include "fft_stream_dispatch.h"
 
 namespace ffb {
 
@@ -65,7 +61,6 @@ struct DimTables {
   cx<T>* twr = nullptr;  // split step: exp(-i pi k / N), k <= N (dim 0 of R2C plans only)
   // four-step split of a long strided line: N = N1*N2, two short sub-passes with wide rows
   bool four = false;
-  bool cluster = false;  // one cluster (DSMEM) kernel instead of the two four-step sub-passes
   int N1 = 0, N2 = 0;
   cx<T>* tw1 = nullptr;  // base twiddles of the length-N1 sub-transform
   cx<T>* tw2 = nullptr;  // base twiddles of the length-N2 sub-transform
@@ -122,14 +117,6 @@ template <typename T> static int fourstep_min() {
   return sizeof(T) == 8 ? 4096 : 8192;
 }
 
-// Cluster (distributed shared memory) four-step kernel: one HBM round trip instead of two, transpose through DSMEM.
-// MEASURED SLOWER than the two-kernel four-step on B200 (N=8192 Float64: 639 us vs 414 us; DSMEM moves ~21 B/clk/SM,
-// about 6 TB/s aggregate, and the two cluster barriers serialise 8 CTAs), so it is opt-in: FFB_CLUSTER_MIN=<min N> enables.
-template <typename T> static int cluster_min() {
-  if (const char* e = getenv("FFB_CLUSTER_MIN")) { const int v = atoi(e); return v > 0 ? v : (1 << 30); }
-  return 1 << 30;
-}
-
 template <typename T>
 static int build_tables(ffb_plan* pl) {
   for (int d = 0; d < pl->ndim; ++d) {
@@ -142,11 +129,9 @@ static int build_tables(ffb_plan* pl) {
     const int np = pow2_radices(N, rad);
     const bool allow = !(pl->flags & FFB_PLAN_FORCE_GENERIC) && is_pow2((uint64_t)N) && N >= 2;
     tb->pow2 = allow && N <= pow2_max_n(sizeof(T)) && np > 0;
-    const bool use_cluster = allow && d > 0 && cluster_has(N) && N >= cluster_min<T>();
-    if (allow && d > 0 && ((N >= fourstep_min<T>() && N <= 65536) || use_cluster)) {
+    if (allow && d > 0 && N >= fourstep_min<T>() && N <= 65536) {
       const int l2 = ilog2((uint64_t)N);
       tb->four = true;
-      tb->cluster = use_cluster;
       tb->N1 = 1 << (l2 / 2);
       tb->N2 = N / tb->N1;
       tb->pow2 = true;
@@ -174,8 +159,7 @@ static int build_tables(ffb_plan* pl) {
       if (rc) return rc;
     }
     char buf[96];
-    if (tb->cluster) snprintf(buf, sizeof(buf), "dim%d:N=%d:pow2-cluster-dsmem-four-step(%dx%d) ", d, N, tb->N1, tb->N2);
-    else if (tb->four) snprintf(buf, sizeof(buf), "dim%d:N=%d:pow2-four-step(%dx%d) ", d, N, tb->N1, tb->N2);
+    if (tb->four) snprintf(buf, sizeof(buf), "dim%d:N=%d:pow2-four-step(%dx%d) ", d, N, tb->N1, tb->N2);
     else snprintf(buf, sizeof(buf), "dim%d:N=%d:%s ", d, N, tb->pow2 ? "pow2-register-stockham" : "generic-mixed-radix");
     pl->desc += buf;
   }
@@ -259,52 +243,6 @@ struct SegStride { int seg = 0; long long stride = 0; };  // seg = 0: unsegmente
 // two-level outer index (four-step sub-passes): blockIdx.y = o_lo + mod*o_hi -> o_lo*os + o_hi*os2
 struct Outer2 { int mod = 0; long long nhi = 1, in_os2 = 0, out_os2 = 0; };
 
-// Streaming kernel thresholds (measured, profiles/r01_stream_*.log); FFB_STREAM_MIN overrides (0 = never)
-static int stream_min_n(size_t real_bytes) {
-  if (const char* e = getenv("FFB_STREAM_MIN")) { const int v = atoi(e); return v > 0 ? v : (1 << 30); }
-  (void)real_bytes;
-  return 1 << 30;   // measured slower than the plain kernel (the passes are issue-bound, not latency-bound): opt-in only
-}
-
-template <typename T>
-static int stream_pass(int N, int dir, const void* in, void* out, long long in_es, long long in_os, long long out_es, long long out_os,
-                       long long nlines, long long nouter, T scale, const cx<T>* tw, cudaStream_t st, SegStride in_seg, SegStride out_seg) {
-  StreamParams<T> p;
-  const int Tn = N / 16;
-  const int maxT = pow2_max_threads(sizeof(T));
-  int W = std::min(sizeof(T) == 8 ? 8 : 16, maxT / Tn);
-  if (const char* e = getenv("FFB_W_STREAM")) { const int w = atoi(e); if (w >= 1 && is_pow2((uint64_t)w) && Tn * w <= maxT) W = w; }
-  while (W > 1 && W / 2 >= nlines) W /= 2;
-  const size_t cap = (size_t)max_smem_optin() - 1024;
-  int split = 1;
-  if constexpr (sizeof(T) == 4) {
-    split = stream_smem_bytes<T, false>(N, W) > cap;
-    if (const char* e = getenv("FFB_STREAM_SPLIT")) split = atoi(e) != 0 || split;
-  }
-  const size_t smem = split ? stream_smem_bytes<T, true>(N, W) : stream_smem_bytes<T, false>(N, W);
-  FFB_REQUIRE(smem <= cap, FFB_EUNSUPPORTED, "streaming pass N=%d W=%d needs %zu bytes of shared memory", N, W, smem);
-  p.in = reinterpret_cast<const cx<T>*>(in); p.out = reinterpret_cast<cx<T>*>(out);
-  p.in_es = in_es; p.in_os = in_os; p.out_es = out_es; p.out_os = out_os;
-  for (int m = 0; m < 16; ++m) {
-    const long long i = (long long)m * Tn;
-    p.in_off[m] = in_seg.seg ? (i % in_seg.seg) * in_es + (i / in_seg.seg) * in_seg.stride : i * in_es;
-    p.out_off[m] = out_seg.seg ? (i % out_seg.seg) * out_es + (i / out_seg.seg) * out_seg.stride : i * out_es;
-  }
-  p.nlines = nlines; p.W = W;
-  const long long gx = (nlines + W - 1) / W;
-  FFB_REQUIRE(gx < (1ll << 31), FFB_EUNSUPPORTED, "too many lines for one launch");
-  p.gx = (int)gx; p.ntiles = gx * nouter;
-  p.scale = scale; p.tw = tw; p.keep_out = g_pass_keep;
-  char pname[64];
-  snprintf(pname, sizeof(pname), "fft_c2c_cols_stream_%s_N%d", sizeof(T) == 8 ? "f64" : "f32", N);
-  ProfScope ps(pname, (double)nlines * (double)nouter * 2.0 * N * sizeof(cx<T>));
-  int rc;
-  if constexpr (sizeof(T) == 8) rc = stream_launch_double(N, dir, split, &p, Tn * W, smem, st);
-  else rc = stream_launch_float(N, dir, split, &p, Tn * W, smem, st);
-  if (rc == 1) return set_error(FFB_EUNSUPPORTED, "no streaming FFT kernel for N=%d", N);
-  return rc;
-}
-
 template <typename T>
 static int pow2_pass(int N, int mode, int dir, const void* in, void* out, long long in_es, long long in_ls, long long in_os,
                      long long out_es, long long out_ls, long long out_os, long long nlines, long long nouter, T scale,
@@ -312,12 +250,6 @@ static int pow2_pass(int N, int mode, int dir, const void* in, void* out, long l
                      Outer2 o2 = Outer2(), const cx<T>* twN = nullptr, int twN_mask = 0,
                      const typename Pow2Params<T>::Fuse* pro = nullptr, const typename Pow2Params<T>::Fuse* epi = nullptr, const T* rmul = nullptr) {
   Pow2Params<T> p;
-  // plain long strided passes: software-pipelined persistent kernel (fft_stream.cuh)
-  if (mode == C2C_COLS && !pro && !epi && !rmul && !o2.mod && in_ls == 1 && out_ls == 1 && stream_has(N) && N >= stream_min_n(sizeof(T))) {
-    const int Tn = N / 16;
-    const bool seg_ok = (!in_seg.seg || in_seg.seg % Tn == 0) && (!out_seg.seg || out_seg.seg % Tn == 0);
-    if (seg_ok) return stream_pass<T>(N, dir, in, out, in_es, in_os, out_es, out_os, nlines, nouter, scale, tw, st, in_seg, out_seg);
-  }
   // plain strided passes: lean kernel variant with host-computed element offsets (needs segment lengths that are multiples of N/R)
   long long lean_out_off[16] = {0};
   static int lean_env = -1;
@@ -461,32 +393,6 @@ static int cols_pass(const DimTables<T>* tb, int part, long long inner, long lon
                         SegStride(), SegStride(), Outer2(), nullptr, 0, pro, epi);
   }
   const int N1 = tb->N1, N2 = tb->N2;
-  if (part == 3) {
-    // cluster kernel: tile = W columns x N rows per cluster of 8 CTAs; slices along blockIdx.y
-    ClusterParams<T> cp;
-    cp.es = inner; cp.os = inner * N; cp.ncols = inner; cp.scale = scale;
-    cp.tw1 = tb->tw1; cp.tw2 = tb->tw2; cp.twN = tb->twN;
-    if (pro) cp.pro = *pro; else cp.pro.on = 0;
-    if (epi) cp.epi = *epi; else cp.epi.on = 0;
-    const int Wc = cluster_cols(sizeof(T));
-    const long long ntiles = (inner + Wc - 1) / Wc;
-    FFB_REQUIRE(ntiles * 8 < (1ll << 31), FFB_EUNSUPPORTED, "too many tiles");
-    char pname[64];
-    snprintf(pname, sizeof(pname), "fft_cluster_%s_N%d", sizeof(T) == 8 ? "f64" : "f32", N);
-    ProfScope ps(pname, (double)inner * (double)outer * 2.0 * N * sizeof(cx<T>));
-    for (long long o0 = 0; o0 < outer; o0 += 65535) {
-      const long long cnt = std::min<long long>(65535, outer - o0);
-      cp.in = src + o0 * cp.os; cp.out = dst + o0 * cp.os;
-      if (pro && pro->w) cp.pro.w = pro->w + o0 * cp.os;
-      if (epi && epi->w) cp.epi.w = epi->w + o0 * cp.os;
-      if (epi && epi->acc) cp.epi.acc = epi->acc + o0 * cp.os;
-      FFB_REQUIRE(o0 == 0 || (!(pro && pro->ko) && !(epi && (epi->ko || epi->ao || epi->loo > 0))), FFB_EUNSUPPORTED, "fused pass with more than 65535 slices");
-      int rc = sizeof(T) == 8 ? cluster_launch_double(N, dir, &cp, ntiles, (int)cnt, st) : cluster_launch_float(N, dir, &cp, ntiles, (int)cnt, st);
-      if (rc == 1) return set_error(FFB_EUNSUPPORTED, "no cluster FFT kernel for N=%d", N);
-      if (rc) return rc;
-    }
-    return FFB_OK;
-  }
   Outer2 o2;
   o2.nhi = outer; o2.in_os2 = inner * N; o2.out_os2 = inner * N;
   if (part == 1) {  // length-N1 transforms over n1 (element stride N2*inner) for each n2, times exp(-/+2 pi i n2 k1/N)
@@ -563,8 +469,7 @@ static int exec_pow2(ffb_plan* pl, const void* in, void* out, int dir, const ffb
   std::vector<Op> ops;
   auto push_cols = [&](int d) {
     auto* tb = reinterpret_cast<DimTables<T>*>(pl->tables[d]);
-    if (tb->cluster) ops.push_back({3, d, 3, false});
-    else if (tb->four) { ops.push_back({3, d, 1, false}); ops.push_back({3, d, 2, true}); }
+    if (tb->four) { ops.push_back({3, d, 1, false}); ops.push_back({3, d, 2, true}); }
     else ops.push_back({3, d, 0, false});
   };
   if (pl->kind == FFB_C2C) { ops.push_back({0, 0, 0, false}); for (int d = 1; d < nd; ++d) push_cols(d); }

@@ -4,7 +4,7 @@ TEST INFRASTRUCTURE ONLY.  This package is a NumPy/SciPy restatement of the refe
 algorithm (FourierFlows.jl v0.10.7, `/root/reference/src/{domains,timesteppers,problem,diffusion}.jl`).
 It may be imported only by `tests/`, `__graft_entry__.smoke()` and the `cpu_baseline` /
 `--impl reference` legs of `bench.py` -- always as the checker or the timed CPU baseline,
-never as part of the product path (`fourierflows.jl_b200/` must not import it).
+never as part of the product path (`fourierflows_jl_b200/` must not import it).
 
 Parity pinning: the reference is pure Julia and cannot run in this image (no `julia`, no FFTW);
 its FFT arithmetic lives in third-party FFTW.jl / cuFFT (no pinned Manifest).  The reference's

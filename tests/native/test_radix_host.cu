@@ -2,7 +2,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
-#include "../../fourierflows.jl_b200/csrc/fft_radix.cuh"
+#include "../../fourierflows_jl_b200/csrc/fft_radix.cuh"
 using namespace ffb;
 
 template <int DIR, int R, int r, int B> struct Run {

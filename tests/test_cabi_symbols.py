@@ -68,7 +68,7 @@ def test_no_cpu_fallback(lib):
 
 def test_product_does_not_import_oracle():
     """The oracle is test infrastructure: nothing under the package may import or execute it."""
-    pkg = os.path.join(ROOT, "fourierflows.jl_b200")
+    pkg = os.path.join(ROOT, "fourierflows_jl_b200")
     for dirpath, _, files in os.walk(pkg):
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h", ".jl")):

@@ -237,19 +237,3 @@ def test_fused_transforms_match_unfused_reference_expressions(ff, shape, T, tol)
         fo.dealias(ref, og)
         plan.mul_ex(outh, dev(ff, zeta), coef=-0.5j, kx=g.kr, m=g.m, alias=alias)
         assert relerr(outh.to_numpy(), ref) <= tol
-
-
-@pytest.mark.parametrize("shape,T,tol", [((64, 4096), np.float64, 1e-12), ((32, 8192), np.float32, 1e-5), ((16, 2048, 4), np.float64, 1e-12),
-                                         ((8, 1024), np.float32, 1e-5)], ids=lambda v: str(v))
-def test_cluster_dsmem_four_step_path(ff, shape, T, tol, monkeypatch):
-    """the opt-in thread-block-cluster kernel (transpose through distributed shared memory) agrees with the oracle"""
-    if not isinstance(shape, tuple):
-        pytest.skip("id helper")
-    monkeypatch.setenv("FFB_CLUSTER_MIN", "1024")
-    rng = np.random.default_rng(41)
-    x = np.asfortranarray(rng.standard_normal(shape).astype(T))
-    plan = ff.Plan(shape, T, ff._lib.FFB_R2C)
-    assert "cluster-dsmem" in plan.describe()
-    xh = plan * dev(ff, x)
-    assert relerr(xh.to_numpy(), fo.RfftPlan(shape, T) * x.astype(np.float64)) <= tol
-    assert relerr(plan.solve(xh).to_numpy(), x) <= tol

@@ -1,4 +1,4 @@
-"""The Julia binding (fourierflows.jl_b200/julia/FourierFlowsB200.jl) cannot be executed in this image (no Julia toolchain);
+"""The Julia binding (fourierflows_jl_b200/julia/FourierFlowsB200.jl) cannot be executed in this image (no Julia toolchain);
 these checks keep it honest statically: every `ccall` names a symbol the header declares and the library exports, with the
 declared number of arguments, and the `struct`s that cross the boundary list the same fields, in the same order, as the C
 header's ctypes mirror."""
@@ -8,7 +8,7 @@ import re
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-JL = open(os.path.join(ROOT, "fourierflows.jl_b200", "julia", "FourierFlowsB200.jl")).read()
+JL = open(os.path.join(ROOT, "fourierflows_jl_b200", "julia", "FourierFlowsB200.jl")).read()
 HDR = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "fourierflows_b200.h")).read(), flags=re.S)
 
 
