@@ -60,7 +60,9 @@ class CProblem:
         self._h = h
         p, cnt = C.c_void_p(), C.c_int64()
         L.call("ffb_problem_sol", self._h, C.byref(p), C.byref(cnt))
-        self.sol = DevArray(self.spectral_shape, cxtype(self.T), ptr=p.value, owner=self)
+        # non-owning view WITHOUT a back-reference: a CProblem <-> sol cycle would leave multi-GB problems to the cyclic GC;
+        # the view is valid while the problem lives, close() invalidates it
+        self.sol = DevArray(self.spectral_shape, cxtype(self.T), ptr=p.value)
 
     @property
     def clock(self):
@@ -102,6 +104,8 @@ class CProblem:
         if getattr(self, "_h", None):
             L.load().ffb_problem_destroy(self._h)
             self._h = None
+            if getattr(self, "sol", None) is not None:
+                self.sol.ptr = None
 
     def __del__(self):
         try:

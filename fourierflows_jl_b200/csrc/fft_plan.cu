@@ -12,6 +12,8 @@
 #include "fft_pow2.cuh"
 #include "fft_pow2_dispatch.h"
 #include "dist.h"
+#include "fft_l2four.cuh"
+#include "fft_l2four_dispatch.h"
 
 namespace ffb {
 
@@ -88,6 +90,9 @@ struct ffb_plan {
   int p2p;                 // exchange mode (FFB_EXCHANGE_*)
   size_t recv_bytes;       // size of each receive buffer
   int p2p_cur;
+  // fused four-step passes (fft_l2four.cuh): L2-resident scratch ring and the ticket / completion counters
+  void* ring; size_t ring_bytes;
+  unsigned* ctr; size_t ctr_count;
 };
 
 namespace ffb {
@@ -379,12 +384,99 @@ static int lean_tile_pass(int N, int dir, int W, const cx<T>* in, long long in_t
   return call_pow2<T>(N, C2C_COLS_LEAN, dir, p, (int)gx, (int)nouter, threads, smem, st);
 }
 
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+// Fused four-step pass (fft_l2four.cuh): both sub-passes in ONE persistent kernel, intermediate in an L2-resident scratch ring.
+// FFB_L2FOUR=0 falls back to the two-kernel form; FFB_L2_CHUNK = chunk width in units of the wider tile (default 1);
+// FFB_L2_AHEAD = tiles of lookahead of A over B in units of 0.1 x resident CTAs (default 20).
+static bool l2four_enabled(int N1, int N2) { return l2four_has(N1, N2) && env_int("FFB_L2FOUR", 1) != 0; }
+
+template <typename T>
+static int l2four_pass(ffb_plan* pl, const DimTables<T>* tb, long long inner, long long outer, const cx<T>* src, cx<T>* dst, int dir, T scale,
+                       cudaStream_t st, typename Pow2Params<T>::Fuse* pro, typename Pow2Params<T>::Fuse* epi) {
+  const int N = tb->N, N1 = tb->N1, N2 = tb->N2;
+  const int WA = kL2FourThreads / (N1 / 16), WB = kL2FourThreads / (N2 / 16), Wmax = std::max(WA, WB);
+  L2FourParams<T> q;
+  memset(&q, 0, sizeof(q));
+  int Wc = Wmax * std::max(1, env_int("FFB_L2_CHUNK", 1));
+  while (Wc > Wmax && Wc / 2 >= inner) Wc /= 2;
+  q.Wc = Wc; q.inner = inner;
+  q.ncc = (int)((inner + Wc - 1) / Wc);
+  FFB_REQUIRE((long long)q.ncc * outer < (1ll << 24), FFB_EUNSUPPORTED, "too many chunks for the fused four-step pass");
+  q.C = (int)(q.ncc * outer);
+  q.tca = Wc / WA; q.tcb = Wc / WB;
+  q.tA = q.tca * N2; q.tB = q.tcb * N1;
+  const size_t smem = std::max(pow2_smem_bytes<T>(N1, WA, C2C_COLS_TW), pow2_smem_bytes<T>(N2, WB, C2C_COLS));
+  auto call = [&](int op, int grid) {
+    return sizeof(T) == 8 ? l2four_call_double(op, N1, N2, dir, &q, grid, smem, st) : l2four_call_float(op, N1, N2, dir, &q, grid, smem, st);
+  };
+  const int per_sm = call(1, 0);
+  FFB_REQUIRE(per_sm >= 1, per_sm < 0 ? per_sm : FFB_EUNSUPPORTED, "fused four-step kernel does not fit an SM (N = %d x %d)", N1, N2);
+  const int resident = per_sm * num_sms();
+  // A runs far enough ahead of B that a B tile's chunk is complete when its ticket is drawn: tiles between the end of A(c)
+  // and the start of B(c) = (D-1)*(tA+tB) + tA >= ahead * resident
+  const double ahead = 0.1 * env_int("FFB_L2_AHEAD", 20);
+  int D = 1 + (int)std::ceil(std::max(0.0, ahead * resident - q.tA) / (double)(q.tA + q.tB));
+  D = std::max(1, std::min(D, q.C));
+  q.D = D; q.nslots = D + 2;
+  q.slot_elems = (long long)N * Wc;
+  const size_t ring_bytes = (size_t)q.nslots * q.slot_elems * sizeof(cx<T>);
+  if (pl->ring_bytes < ring_bytes) {
+    if (pl->ring) { FFB_CUDA(cudaStreamSynchronize(st)); cudaFree(pl->ring); pl->ring = nullptr; pl->ring_bytes = 0; }
+    int rc = ffb_malloc(&pl->ring, ring_bytes);
+    if (rc) return rc;
+    pl->ring_bytes = ring_bytes;
+  }
+  const size_t nctr = 2 + 2 * (size_t)q.C;
+  if (pl->ctr_count < nctr) {
+    if (pl->ctr) { FFB_CUDA(cudaStreamSynchronize(st)); cudaFree(pl->ctr); pl->ctr = nullptr; pl->ctr_count = 0; }
+    void* c = nullptr;
+    int rc = ffb_malloc(&c, nctr * sizeof(unsigned));
+    if (rc) return rc;
+    pl->ctr = reinterpret_cast<unsigned*>(c); pl->ctr_count = nctr;
+    FFB_CUDA(cudaMemsetAsync(pl->ctr, 0, nctr * sizeof(unsigned), st));   // afterwards the kernel leaves the counters zeroed
+  }
+  q.ring = reinterpret_cast<cx<T>*>(pl->ring);
+  q.ctr = pl->ctr;
+  auto base = [&](Pow2Params<T>& p) {
+    p.pro.on = 0; p.epi.on = 0; p.rmul = nullptr; p.reverse = 0; p.pf_ahead = 0;
+    p.in_seg_mask = p.out_seg_mask = 0x7fffffff; p.in_seg_shift = p.out_seg_shift = 31; p.in_seg_stride = p.out_seg_stride = 0;
+    p.in_ls = p.out_ls = 1; p.nlines = inner; p.twr = nullptr; p.twN = nullptr; p.twN_mask = 0;
+  };
+  // A: N1-point transforms over n1 (stride N2*inner) for each n2 = o_lo, output k1 in place of n1, into the scratch chunk [N][Wc]
+  base(q.a);
+  q.a.in = src; q.a.out = nullptr;
+  q.a.in_es = (long long)N2 * inner; q.a.in_os = inner; q.a.in_os2 = inner * N;
+  q.a.out_es = (long long)N2 * Wc; q.a.out_os = Wc; q.a.out_os2 = 0;
+  q.a.outer_mod = N2; q.a.W = WA; q.a.scale = T(1); q.a.tw = tb->tw1; q.a.twN = tb->twN; q.a.twN_mask = N - 1; q.a.keep_out = 1;
+  if (pro) { pro->idm = N2; pro->ido = 1; q.a.pro = *pro; }
+  // B: N2-point transforms over n2 (scratch stride Wc) for each k1 = o_lo (scratch stride N2*Wc), output index k1 + N1*k2
+  base(q.b);
+  q.b.in = nullptr; q.b.out = dst;
+  q.b.in_es = Wc; q.b.in_os = (long long)N2 * Wc; q.b.in_os2 = 0;
+  q.b.out_es = (long long)N1 * inner; q.b.out_os = inner; q.b.out_os2 = inner * N;
+  q.b.outer_mod = N1; q.b.W = WB; q.b.scale = scale; q.b.tw = tb->tw2; q.b.keep_out = 0;
+  if (epi) { epi->idm = N1; epi->ido = 1; q.b.epi = *epi; }
+  char pname[64];
+  snprintf(pname, sizeof(pname), "fft_l2four_%s_N%d", sizeof(T) == 8 ? "f64" : "f32", N);
+  const double lines = (double)inner * (double)outer;
+  const double fused_bytes = lines * N * ((pro && pro->w ? sizeof(T) : 0) + (epi && epi->w ? sizeof(T) : 0) + (epi && epi->acc ? sizeof(cx<T>) : 0));
+  ProfScope ps(pname, lines * 2.0 * N * sizeof(cx<T>) + fused_bytes);
+  const long long total = (long long)q.C * (q.tA + q.tB);
+  int rc = call(0, (int)std::min<long long>(resident, total));
+  return rc == 1 ? set_error(FFB_EUNSUPPORTED, "no fused four-step kernel for N = %d x %d", N1, N2) : rc;
+}
+
 // strided (column) pass along dimension d: one register-resident pass, or the four-step pair A (in place allowed) + B
 // (strictly out of place).  part: 0 = single pass, 1 = four-step A, 2 = four-step B.
 template <typename T>
-static int cols_pass(const DimTables<T>* tb, int part, long long inner, long long outer, const cx<T>* src, cx<T>* dst, int dir, T scale,
+static int cols_pass(ffb_plan* pl, const DimTables<T>* tb, int part, long long inner, long long outer, const cx<T>* src, cx<T>* dst, int dir, T scale,
                      cudaStream_t st, typename Pow2Params<T>::Fuse* pro = nullptr, typename Pow2Params<T>::Fuse* epi = nullptr) {
   const int N = tb->N;
+  if (part == 4) return l2four_pass<T>(pl, tb, inner, outer, src, dst, dir, scale, st, pro, epi);
   if (part == 0) {
     // single pass: transform index = t + m*Tn, the outer slice index is o_lo
     if (pro) { pro->idm = 1; pro->ido = 0; if (pro->other_from_col == 0) pro->other_from_col = 2; }
@@ -447,7 +539,7 @@ static int c2c_dim(ffb_plan* pl, int d, const long long e[3], long long nb, cons
   if (tb->pow2 && tb->tw) {
     if (d == 0)
       return pow2_pass<T>(N, C2C_ROWS, dir, src, dst, 1, N, 0, 1, N, 0, outer, 1, scale, tb->tw, nullptr, st);
-    return cols_pass<T>(tb, 0, inner, outer, src, dst, dir, scale, st);
+    return cols_pass<T>(pl, tb, 0, inner, outer, src, dst, dir, scale, st);
   }
   FFB_REQUIRE(tb->wN, FFB_EUNSUPPORTED, "dimension %d of this plan mixes the arbitrary-size path with a four-step-only length", d);
   int rc = ensure_ws(pl, 2);
@@ -469,7 +561,8 @@ static int exec_pow2(ffb_plan* pl, const void* in, void* out, int dir, const ffb
   std::vector<Op> ops;
   auto push_cols = [&](int d) {
     auto* tb = reinterpret_cast<DimTables<T>*>(pl->tables[d]);
-    if (tb->four) { ops.push_back({3, d, 1, false}); ops.push_back({3, d, 2, true}); }
+    if (tb->four && l2four_enabled(tb->N1, tb->N2)) ops.push_back({3, d, 4, false});   // fused, L2-resident intermediate, in place allowed
+    else if (tb->four) { ops.push_back({3, d, 1, false}); ops.push_back({3, d, 2, true}); }
     else ops.push_back({3, d, 0, false});
   };
   if (pl->kind == FFB_C2C) { ops.push_back({0, 0, 0, false}); for (int d = 1; d < nd; ++d) push_cols(d); }
@@ -523,7 +616,7 @@ static int exec_pow2(ffb_plan* pl, const void* in, void* out, int dir, const ffb
       typename Pow2Params<T>::Fuse* epi = nullptr;
       if (want_pro && i == 0) { hook = make_hook<T>(fuse, op.d, nd, e, false); pro = &hook; }
       if (fuse && dir < 0 && i == n - 1) { hook = make_hook<T>(fuse, op.d, nd, e, true); epi = &hook; }
-      rc = cols_pass<T>(reinterpret_cast<DimTables<T>*>(pl->tables[op.d]), op.part, inner, outer, reinterpret_cast<const cx<T>*>(s_),
+      rc = cols_pass<T>(pl, reinterpret_cast<DimTables<T>*>(pl->tables[op.d]), op.part, inner, outer, reinterpret_cast<const cx<T>*>(s_),
                         reinterpret_cast<cx<T>*>(d_), dir, sc, st, pro, epi);
     }
     g_pass_reverse = 0; g_pass_keep = 0;
@@ -827,6 +920,7 @@ int ffb_plan_create(ffb_plan** out, int ndim, const int64_t* n, int dtype, int k
   pl->ndim = ndim; pl->dtype = dtype; pl->kind = kind; pl->nbatch = nbatch; pl->flags = flags;
   pl->dist = nullptr; pl->nyl = pl->nzl = 0; pl->nchunks = 1;
   pl->recv[0] = pl->recv[1] = nullptr; pl->p2p = 0; pl->p2p_cur = 0; pl->recv_bytes = 0;
+  pl->ring = nullptr; pl->ring_bytes = 0; pl->ctr = nullptr; pl->ctr_count = 0;
   for (int b = 0; b < 2; ++b) for (int q = 0; q < 8; ++q) pl->peers[b][q] = nullptr;
   for (int d = 0; d < 3; ++d) { pl->n[d] = d < ndim ? n[d] : 1; pl->nc[d] = pl->n[d]; pl->tables[d] = nullptr; pl->ws[d] = nullptr; }
   if (kind == FFB_R2C) pl->nc[0] = pl->n[0] / 2 + 1;
@@ -936,6 +1030,7 @@ int ffb_plan_destroy(ffb_plan* pl) {
   if (!pl) return FFB_OK;
   if (pl->dtype == FFB_F64) free_tables<double>(pl); else free_tables<float>(pl);
   for (int i = 0; i < 3; ++i) cudaFree(pl->ws[i]);
+  cudaFree(pl->ring); cudaFree(pl->ctr);
   if (pl->recv[0]) {
     std::lock_guard<std::mutex> lk(g_recv_mu);
     for (auto& r : g_recv_pool)

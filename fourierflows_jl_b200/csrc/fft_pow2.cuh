@@ -229,6 +229,15 @@ template <typename T> FFB_D void stk(cx<T>* p, cx<T> c, int keep) {
   if (keep) *reinterpret_cast<V*>(p) = q; else __stcs(reinterpret_cast<V*>(p), q);
 }
 
+template <typename T> FFB_D cx<T> ldg_cg(const cx<T>* p) {
+  using V = typename vec2<T>::type;
+  V q = __ldcg(reinterpret_cast<const V*>(p));
+  return mk<T>(q.x, q.y);
+}
+template <typename T, bool CG> FFB_D cx<T> ldin(const cx<T>* p) {
+  if constexpr (CG) return ldg_cg(p); else return ldc(p);
+}
+
 FFB_D void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // factor (cr + i ci) * k0[i0] * kt[it] * ko[io] * w[off], evaluated left to right like `im * kr * invKrsq * sol`
@@ -242,8 +251,13 @@ FFB_D cx<T> fuse_factor(T cr, T ci, const T* k0, const T* kt, const T* ko, const
   return mk<T>(fr, fi);
 }
 
-template <typename T, int DIR, int MODE, int MAXT, int MINB, int R, int... Rs>
-__global__ void __launch_bounds__(MAXT, MINB) fft_pow2_kernel(const Pow2Params<T> p) {
+// One tile (W lines) of a pass.  (bx, by) = tile coordinates (blockIdx of the plain launch), gdx / gdy = extents of the tile
+// grid, pin / pout = array bases (p.in / p.out for the plain launch; the persistent fused four-step kernel of fft_l2four.cuh
+// substitutes its L2-resident scratch ring), nlines = first inactive line.  IN_CG: load the input with ld.global.cg (L2 only):
+// data written by other CTAs of the SAME kernel must not be served from a stale L1 line.
+template <typename T, int DIR, int MODE, bool IN_CG, int R, int... Rs>
+FFB_D void fft_pow2_tile(const Pow2Params<T>& p, const unsigned bx, const unsigned by, const unsigned gdx, const unsigned gdy, const void* pin,
+                         void* pout, const long long nlines) {
   constexpr int N = radix_product<Rs...>::value;
   constexpr int Tn = N / R;
   constexpr bool COLS = (MODE == C2C_COLS || MODE == C2C_COLS_TW || MODE == C2C_COLS_LEAN);
@@ -257,10 +271,8 @@ __global__ void __launch_bounds__(MAXT, MINB) fft_pow2_kernel(const Pow2Params<T
   const int tid = threadIdx.x;
   const int w = COLS ? tid % W : tid / Tn;
   const int t = COLS ? tid / W : tid % Tn;
-  const unsigned bx = p.reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
-  const unsigned by = p.reverse ? gridDim.y - 1 - blockIdx.y : blockIdx.y;
   const long long line = (long long)bx * W + w;
-  const bool active = line < p.nlines;
+  const bool active = line < nlines;
   const int o_lo = (int)(by % (unsigned)p.outer_mod);
   const long long o_hi = by / (unsigned)p.outer_mod;
 
@@ -300,8 +312,8 @@ __global__ void __launch_bounds__(MAXT, MINB) fft_pow2_kernel(const Pow2Params<T
   if constexpr (!COLS) {
     if (p.pf_ahead > 0) {
       const long long pl = line + (long long)p.pf_ahead * W;
-      if (pl < p.nlines) {
-        const char* base = reinterpret_cast<const char*>(reinterpret_cast<const cx<T>*>(p.in) + pl * p.in_ls);
+      if (pl < nlines) {
+        const char* base = reinterpret_cast<const char*>(reinterpret_cast<const cx<T>*>(pin) + pl * p.in_ls);
         constexpr int line_bytes = (MODE == C2R_ROWS ? (N + 1) : N) * (int)sizeof(cx<T>);
 #pragma unroll 1
         for (int off = t * 128; off < line_bytes; off += Tn * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
@@ -311,7 +323,7 @@ __global__ void __launch_bounds__(MAXT, MINB) fft_pow2_kernel(const Pow2Params<T
   // ---------------- load ----------------
   if constexpr (MODE == C2R_ROWS) {
     // Z[k] = (X[k] + conj(X[N-k])) + i*exp(+i*pi*k/N)*(X[k] - conj(X[N-k]))
-    const cx<T>* in = reinterpret_cast<const cx<T>*>(p.in) + o_lo * p.in_os + o_hi * p.in_os2 + line * p.in_ls;
+    const cx<T>* in = reinterpret_cast<const cx<T>*>(pin) + o_lo * p.in_os + o_hi * p.in_os2 + line * p.in_ls;
     const cx<T> wbase = load_tw<T, -1>(p.twr + t);
     // all loads of X[k] first, then the partners X[N-k] in batches: independent loads are in flight together
 #pragma unroll
@@ -333,31 +345,31 @@ __global__ void __launch_bounds__(MAXT, MINB) fft_pow2_kernel(const Pow2Params<T
       });
     });
   } else if constexpr (LEAN) {
-    const cx<T>* in = reinterpret_cast<const cx<T>*>(p.in) + (long long)by * p.in_os + (long long)bx * p.in_ts + w + (long long)t * p.in_es;
+    const cx<T>* in = reinterpret_cast<const cx<T>*>(pin) + (long long)by * p.in_os + (long long)bx * p.in_ts + w + (long long)t * p.in_es;
 #pragma unroll
-    for (int m = 0; m < R; ++m) v[m] = active ? ldc(in + p.in_off[m]) : mk<T>(0, 0);
+    for (int m = 0; m < R; ++m) v[m] = active ? ldin<T, IN_CG>(in + p.in_off[m]) : mk<T>(0, 0);
     // one CTA per SM runs its load / butterfly / store phases back to back: pull the tile that starts `pf_ahead` CTAs later
     // into L2 while this one computes, so that its load phase is an L2 hit
     if (p.pf_ahead > 0) {
-      const long long lt = (long long)by * gridDim.x + bx + p.pf_ahead;
-      const long long pby = lt / gridDim.x, pbx = lt % gridDim.x;
-      if (pby < gridDim.y && pbx * W + w < p.nlines) {
-        const cx<T>* pin = reinterpret_cast<const cx<T>*>(p.in) + pby * p.in_os + pbx * p.in_ts + w + (long long)t * p.in_es;
+      const long long lt = (long long)by * gdx + bx + p.pf_ahead;
+      const long long pby = lt / gdx, pbx = lt % gdx;
+      if (pby < gdy && pbx * W + w < nlines) {
+        const cx<T>* pfp = reinterpret_cast<const cx<T>*>(pin) + pby * p.in_os + pbx * p.in_ts + w + (long long)t * p.in_es;
 #pragma unroll
-        for (int m = 0; m < R; ++m) prefetch_l2(pin + p.in_off[m]);
+        for (int m = 0; m < R; ++m) prefetch_l2(pfp + p.in_off[m]);
       }
     }
   } else {
-    const cx<T>* in = reinterpret_cast<const cx<T>*>(p.in) + o_lo * p.in_os + o_hi * p.in_os2 + line * p.in_ls;
+    const cx<T>* in = reinterpret_cast<const cx<T>*>(pin) + o_lo * p.in_os + o_hi * p.in_os2 + line * p.in_ls;
 #pragma unroll
     for (int m = 0; m < R; ++m) {
       const int i = t + m * Tn;
-      v[m] = active ? ldc(in + (long long)(i & p.in_seg_mask) * p.in_es + (long long)(i >> p.in_seg_shift) * p.in_seg_stride) : mk<T>(0, 0);
+      v[m] = active ? ldin<T, IN_CG>(in + (long long)(i & p.in_seg_mask) * p.in_es + (long long)(i >> p.in_seg_shift) * p.in_seg_stride) : mk<T>(0, 0);
     }
     if (p.pro.on && active) {
       const int i0 = (int)(line % p.pro.n0);
       const long long io = p.pro.other_from_col == 1 ? line / p.pro.n0 : (p.pro.other_from_col == 2 ? (long long)o_lo : o_hi);
-      const long long base = (in - reinterpret_cast<const cx<T>*>(p.in));
+      const long long base = (in - reinterpret_cast<const cx<T>*>(pin));
       // the dense factor is loaded in batches (independent loads first, uses after) so its latency is paid once per batch
       constexpr int PB = R < 8 ? R : 8;
 #pragma unroll
@@ -395,7 +407,7 @@ __global__ void __launch_bounds__(MAXT, MINB) fft_pow2_kernel(const Pow2Params<T
       if constexpr (PL == 2) xb[plane + addr(t + m * Tn)] = xget<T, 1>(v[m]);
     }
     __syncthreads();
-    cx<T>* out = reinterpret_cast<cx<T>*>(p.out) + o_lo * p.out_os + o_hi * p.out_os2 + line * p.out_ls;
+    cx<T>* out = reinterpret_cast<cx<T>*>(pout) + o_lo * p.out_os + o_hi * p.out_os2 + line * p.out_ls;
     const T half = T(0.5);
     const cx<T> wbase = load_tw<T, -1>(p.twr + t);
     static_for<0, R>([&](auto M) {
@@ -415,7 +427,7 @@ __global__ void __launch_bounds__(MAXT, MINB) fft_pow2_kernel(const Pow2Params<T
     });
   } else if constexpr (MODE == C2R_ROWS) {
     if (active) {
-      cx<T>* out = reinterpret_cast<cx<T>*>(p.out) + o_lo * p.out_os + o_hi * p.out_os2 + line * p.out_ls;
+      cx<T>* out = reinterpret_cast<cx<T>*>(pout) + o_lo * p.out_os + o_hi * p.out_os2 + line * p.out_ls;
       const T sc = p.scale;
       if (p.rmul) {
         const cx<T>* mulp = reinterpret_cast<const cx<T>*>(p.rmul) + o_lo * p.out_os + o_hi * p.out_os2 + line * p.out_ls;
@@ -459,13 +471,13 @@ __global__ void __launch_bounds__(MAXT, MINB) fft_pow2_kernel(const Pow2Params<T
       }
     }
     if (active) {
-      cx<T>* out = reinterpret_cast<cx<T>*>(p.out) + o_lo * p.out_os + o_hi * p.out_os2 + line * p.out_ls;
+      cx<T>* out = reinterpret_cast<cx<T>*>(pout) + o_lo * p.out_os + o_hi * p.out_os2 + line * p.out_ls;
       const T sc = p.scale;
       auto off = [&](int i) { return (long long)(i & p.out_seg_mask) * p.out_es + (long long)(i >> p.out_seg_shift) * p.out_seg_stride; };
       if (p.epi.on) {
         const int i0 = (int)(line % p.epi.n0);
         const long long io = p.epi.other_from_col == 1 ? line / p.epi.n0 : (p.epi.other_from_col == 2 ? (long long)o_lo : o_hi);
-        const long long base = (out - reinterpret_cast<cx<T>*>(p.out));
+        const long long base = (out - reinterpret_cast<cx<T>*>(pout));
         const bool dead0 = p.epi.dealias && ((p.epi.lo0 > 0 && i0 >= p.epi.lo0 - 1 && i0 < p.epi.hi0) || (p.epi.loo > 0 && io >= p.epi.loo - 1 && io < p.epi.hio));
         constexpr int EB = R < 4 ? R : 4;
 #pragma unroll
@@ -501,6 +513,13 @@ __global__ void __launch_bounds__(MAXT, MINB) fft_pow2_kernel(const Pow2Params<T
       }
     }
   }
+}
+
+template <typename T, int DIR, int MODE, int MAXT, int MINB, int R, int... Rs>
+__global__ void __launch_bounds__(MAXT, MINB) fft_pow2_kernel(const __grid_constant__ Pow2Params<T> p) {
+  const unsigned bx = p.reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
+  const unsigned by = p.reverse ? gridDim.y - 1 - blockIdx.y : blockIdx.y;
+  fft_pow2_tile<T, DIR, MODE, false, R, Rs...>(p, bx, by, gridDim.x, gridDim.y, p.in, p.out, p.nlines);
 }
 
 // shared-memory bytes needed by a launch with W lines per CTA (the r2c split step stages full complex values)

@@ -416,6 +416,8 @@ def getetdcoeffs(dt, L, ncirc=32, rcirc=1):
     Larr = np.asarray(L)
     circ = (rcirc * np.exp(2j * np.pi / ncirc * (np.arange(ncirc) + 0.5))).astype(np.complex128)
     dtL = np.asarray(dt * Larr)  # in the precision of dt*L, as in `dt * L .+ circ`
+    if dtL.size > (1 << 20):
+        return _getetdcoeffs_chunked(dt, dtL, circ, np.iscomplexobj(Larr))
     zc = dtL[..., None].astype(np.complex128) + circ.reshape((1,) * dtL.ndim + (ncirc,))
     ez, ez2 = np.exp(zc), np.exp(zc / 2)
     zc2 = zc * zc
@@ -431,6 +433,35 @@ def getetdcoeffs(dt, L, ncirc=32, rcirc=1):
             v = v.real
         out.append(np.asfortranarray(v) if np.ndim(v) else v[()])
     return tuple(out)
+
+
+def _getetdcoeffs_chunked(dt, dtL, circ, cplx):
+    """Same arithmetic as `getetdcoeffs`, element by element, for arrays whose (size x 32) contour temporaries would not fit
+    host memory (8192^2: 17 GB each): 1 Mi-element chunks on a thread pool (NumPy releases the GIL), the contour mean
+    accumulated point by point."""
+    from concurrent.futures import ThreadPoolExecutor
+    flat = np.ravel(dtL, order="F")
+    outs = [np.empty(flat.size, dtype=np.complex128 if cplx else np.float64) for _ in range(4)]
+    n = len(circ)
+
+    def work(lo):
+        z0 = flat[lo:lo + (1 << 20)].astype(np.complex128)
+        acc = [np.zeros(z0.size, dtype=np.complex128) for _ in range(4)]
+        for j in range(n):
+            zc = z0 + circ[j]
+            ez, ez2 = np.exp(zc), np.exp(zc / 2)
+            zc2 = zc * zc
+            zc3 = zc2 * zc
+            acc[0] += (ez2 - 1) / zc
+            acc[1] += (-4 - zc + ez * (4 - 3 * zc + zc2)) / zc3
+            acc[2] += (2 + zc + ez * (-2 + zc)) / zc3
+            acc[3] += (-4 - 3 * zc - zc2 + ez * (4 - zc)) / zc3
+        for o, a in zip(outs, acc):
+            v = dt * (a / n)
+            o[lo:lo + z0.size] = v if cplx else v.real
+    with ThreadPoolExecutor(max(1, _WORKERS)) as ex:
+        list(ex.map(work, range(0, flat.size, 1 << 20)))
+    return tuple(np.asfortranarray(o.reshape(dtL.shape, order="F")) for o in outs)
 
 
 def TimeStepper(stepper: str, eqn: Equation, dt=None, **filterkwargs) -> _Stepper:

@@ -57,3 +57,32 @@ def test_reference_arm_other_ranks_exit_quietly():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
                        capture_output=True, text=True, env=env, timeout=120)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_both_arms_describe_the_same_config(bench):
+    """the driver compares the `config` of the two arms: it must not depend on which arm printed it"""
+    class A:
+        workload, n, n3, nz_per_gpu = "auto", 8192, 2048, 256
+    for world in (1, 2, 8):
+        a, b = bench.make_workload(A(), world), bench.make_workload(A(), world)
+        assert a.config() == b.config() and set(a.config()) == {"workload", "grid", "stepper", "precision"}
+    A.workload = "c4"
+    w = bench.make_workload(A(), 4)
+    assert tuple(w.shape) == (1024, 1024, 1024) and w.stepper == "FilteredRK4" and w.scaling == "strong" and np.dtype(w.T) == np.float64
+    A.workload = "c5-lsrk54"
+    w = bench.make_workload(A(), 8)
+    assert tuple(w.shape) == (2048, 2048, 2048) and w.stepper == "LSRK54" and np.dtype(w.T) == np.float32
+
+
+def test_byte_model_matches_survey_8d(bench):
+    """C4 = 752.8 GB/step, C5-LSRK54 = 3696.6 GB/step, C5-ETDRK4 = 2922.9 GB/step, C2 = 2.148 GB"""
+    class A:
+        workload, n, n3, nz_per_gpu = "c4", 8192, 2048, 256
+    assert abs(bench.make_workload(A(), 1).bytes_per_step()[0] / 1e9 - 752.8) < 1.0
+    A.workload = "c5-lsrk54"
+    # the first LSRK54 stage folds `S2 = 0` (one array less than SURVEY's 5 x 5.5 S): 34.4 GB fewer, the conservative count
+    assert 0 <= 3696.6 - bench.make_workload(A(), 8).bytes_per_step()[0] / 1e9 < 36.0
+    A.workload = "c5"
+    assert abs(bench.make_workload(A(), 8).bytes_per_step()[0] / 1e9 - 2922.9) < 3.0
+    A.workload = "c2"
+    assert abs(bench.make_workload(A(), 1).bytes_per_step()[0] / 1e9 - 2.148) < 0.01

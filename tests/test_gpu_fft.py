@@ -237,3 +237,43 @@ def test_fused_transforms_match_unfused_reference_expressions(ff, shape, T, tol)
         fo.dealias(ref, og)
         plan.mul_ex(outh, dev(ff, zeta), coef=-0.5j, kx=g.kr, m=g.m, alias=alias)
         assert relerr(outh.to_numpy(), ref) <= tol
+
+
+@pytest.mark.parametrize("T,tol", [(np.float64, 1e-12), (np.float32, 1e-5)], ids=["f64", "f32"])
+@pytest.mark.parametrize("shape", [(64, 1024), (66, 2048), (128, 4096), (32, 8192), (16, 16384), (32, 1024, 8), (16, 8, 2048), (8, 4096, 2)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_fused_l2_four_step_matches_two_kernel_form_and_oracle(ff, shape, T, tol, monkeypatch):
+    """The persistent fused four-step pass (both sub-passes in one kernel, intermediate in an L2-resident ring; every
+    instantiated N1 x N2 split, ragged column chunks, outer slices, in-place execution) against the oracle, and bit-for-bit
+    against the two-kernel four-step it replaces (same arithmetic, different schedule)."""
+    monkeypatch.setenv("FFB_FOURSTEP_MIN", "1024")
+    if T == np.float64 and max(shape[1:]) > 8192:
+        pytest.skip("Float64 register kernels stop at 8192; 16384 = 128 x 128 is covered in Float32")
+    rng = np.random.default_rng(43)
+    x = np.asfortranarray(rng.standard_normal(shape).astype(T))
+    ref = fo.RfftPlan(shape, T) * x.astype(np.float64)
+    outs = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("FFB_L2FOUR", mode)
+        plan = ff.Plan(shape, T, ff._lib.FFB_R2C)
+        assert "four-step" in plan.describe()
+        xh = plan * dev(ff, x)
+        outs[mode] = xh.to_numpy()
+        assert relerr(outs[mode], ref) <= tol
+        back = plan.solve(xh)
+        assert relerr(back.to_numpy(), x) <= tol
+        assert np.array_equal(xh.to_numpy(), outs[mode]), "the inverse transform must preserve its input"
+    assert np.array_equal(outs["1"], outs["0"])
+    # twice in a row on one plan: the kernel leaves its ticket / completion counters zeroed
+    monkeypatch.setenv("FFB_L2FOUR", "1")
+    plan = ff.Plan(shape, T, ff._lib.FFB_R2C)
+    a = (plan * dev(ff, x)).to_numpy()
+    b = (plan * dev(ff, x)).to_numpy()
+    assert np.array_equal(a, b) and np.array_equal(a, outs["1"])
+    # complex plan, in place
+    cT = np.complex64 if T == np.float32 else np.complex128
+    z = np.asfortranarray((rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).astype(cT))
+    cplan = ff.Plan(shape, T, ff._lib.FFB_C2C)
+    dz = dev(ff, z)
+    cplan.mul(dz, dz)
+    assert relerr(dz.to_numpy(), np.fft.fftn(z.astype(np.complex128))) <= tol
