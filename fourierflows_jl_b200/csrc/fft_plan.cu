@@ -92,7 +92,7 @@ struct ffb_plan {
   int p2p_cur;
   // fused four-step passes (fft_l2four.cuh): L2-resident scratch ring and the ticket / completion counters
   void* ring; size_t ring_bytes;
-  unsigned* ctr; size_t ctr_count;
+  unsigned* ctr; size_t ctr_count; int ctr_C;
 };
 
 namespace ffb {
@@ -401,14 +401,20 @@ static int l2four_pass(ffb_plan* pl, const DimTables<T>* tb, long long inner, lo
   const int WA = kL2FourThreads / (N1 / 16), WB = kL2FourThreads / (N2 / 16), Wmax = std::max(WA, WB);
   L2FourParams<T> q;
   memset(&q, 0, sizeof(q));
-  int Wc = Wmax * std::max(1, env_int("FFB_L2_CHUNK", 1));
+  int Wc = Wmax * std::max(1, env_int("FFB_L2_CHUNK", 2));
+  FFB_REQUIRE(is_pow2((uint64_t)Wc), FFB_EINVAL, "FFB_L2_CHUNK must be a power of two");
   while (Wc > Wmax && Wc / 2 >= inner) Wc /= 2;
   q.Wc = Wc; q.inner = inner;
   q.ncc = (int)((inner + Wc - 1) / Wc);
-  FFB_REQUIRE((long long)q.ncc * outer < (1ll << 24), FFB_EUNSUPPORTED, "too many chunks for the fused four-step pass");
+  FFB_REQUIRE((long long)q.ncc * outer < (1ll << 22), FFB_EUNSUPPORTED, "too many chunks for the fused four-step pass");
   q.C = (int)(q.ncc * outer);
-  q.tca = Wc / WA; q.tcb = Wc / WB;
-  q.tA = q.tca * N2; q.tB = q.tcb * N1;
+  q.Cpad = (q.C + 3) / 4 * 4;
+  q.lgWA = ilog2((uint64_t)WA); q.lgWB = ilog2((uint64_t)WB);
+  q.lg_tca = ilog2((uint64_t)(Wc / WA)); q.lg_tcb = ilog2((uint64_t)(Wc / WB));
+  const int tiles = (Wc / WA) * N2;   // == (Wc / WB) * N1
+  q.lgT = ilog2((uint64_t)tiles);
+  FFB_REQUIRE((1 << q.lgT) == tiles && (Wc / WB) * N1 == tiles, FFB_EUNSUPPORTED, "internal: tile counts of the two sub-passes differ");
+  FFB_REQUIRE(((long long)q.C << (q.lgT + 1)) < (1ll << 31), FFB_EUNSUPPORTED, "too many tiles for the fused four-step pass");
   const size_t smem = std::max(pow2_smem_bytes<T>(N1, WA, C2C_COLS_TW), pow2_smem_bytes<T>(N2, WB, C2C_COLS));
   auto call = [&](int op, int grid) {
     return sizeof(T) == 8 ? l2four_call_double(op, N1, N2, dir, &q, grid, smem, st) : l2four_call_float(op, N1, N2, dir, &q, grid, smem, st);
@@ -416,12 +422,14 @@ static int l2four_pass(ffb_plan* pl, const DimTables<T>* tb, long long inner, lo
   const int per_sm = call(1, 0);
   FFB_REQUIRE(per_sm >= 1, per_sm < 0 ? per_sm : FFB_EUNSUPPORTED, "fused four-step kernel does not fit an SM (N = %d x %d)", N1, N2);
   const int resident = per_sm * num_sms();
-  // A runs far enough ahead of B that a B tile's chunk is complete when its ticket is drawn: tiles between the end of A(c)
-  // and the start of B(c) = (D-1)*(tA+tB) + tA >= ahead * resident
+  // A runs far enough ahead of B that a chunk is complete when the first tile that needs it starts: at that moment the oldest
+  // unfinished ticket is about one wave of resident CTAs behind, so the tickets between the end of A(c) and the start of B(c),
+  // (2D - 1) * tiles, must exceed `ahead` waves; the same distance separates B(c) from the A(c + nslots) that reuses its slot.
   const double ahead = 0.1 * env_int("FFB_L2_AHEAD", 20);
-  int D = 1 + (int)std::ceil(std::max(0.0, ahead * resident - q.tA) / (double)(q.tA + q.tB));
+  int D = (int)std::ceil((ahead * resident / tiles + 1.0) / 2.0);
   D = std::max(1, std::min(D, q.C));
-  q.D = D; q.nslots = D + 2;
+  q.D = D;
+  q.nslots = D + (int)std::ceil((ahead * resident / tiles + 1.0) / 2.0) + 1;
   q.slot_elems = (long long)N * Wc;
   const size_t ring_bytes = (size_t)q.nslots * q.slot_elems * sizeof(cx<T>);
   if (pl->ring_bytes < ring_bytes) {
@@ -430,17 +438,23 @@ static int l2four_pass(ffb_plan* pl, const DimTables<T>* tb, long long inner, lo
     if (rc) return rc;
     pl->ring_bytes = ring_bytes;
   }
-  const size_t nctr = 2 + 2 * (size_t)q.C;
+  const size_t nctr = 4 + 2 * (size_t)q.Cpad + 4;
   if (pl->ctr_count < nctr) {
     if (pl->ctr) { FFB_CUDA(cudaStreamSynchronize(st)); cudaFree(pl->ctr); pl->ctr = nullptr; pl->ctr_count = 0; }
     void* c = nullptr;
     int rc = ffb_malloc(&c, nctr * sizeof(unsigned));
     if (rc) return rc;
     pl->ctr = reinterpret_cast<unsigned*>(c); pl->ctr_count = nctr;
-    FFB_CUDA(cudaMemsetAsync(pl->ctr, 0, nctr * sizeof(unsigned), st));   // afterwards the kernel leaves the counters zeroed
+  }
+  if (pl->ctr_C != q.Cpad) {
+    // counter layout depends on the chunk count: start from zero (afterwards every launch leaves the counters zeroed)
+    FFB_CUDA(cudaMemsetAsync(pl->ctr, 0, pl->ctr_count * sizeof(unsigned), st));
+    pl->ctr_C = q.Cpad;
   }
   q.ring = reinterpret_cast<cx<T>*>(pl->ring);
   q.ctr = pl->ctr;
+  q.pf = env_int("FFB_L2_PF", 1);
+  q.acq = env_int("FFB_L2_ACQ", 1);
   auto base = [&](Pow2Params<T>& p) {
     p.pro.on = 0; p.epi.on = 0; p.rmul = nullptr; p.reverse = 0; p.pf_ahead = 0;
     p.in_seg_mask = p.out_seg_mask = 0x7fffffff; p.in_seg_shift = p.out_seg_shift = 31; p.in_seg_stride = p.out_seg_stride = 0;
@@ -465,8 +479,24 @@ static int l2four_pass(ffb_plan* pl, const DimTables<T>* tb, long long inner, lo
   const double lines = (double)inner * (double)outer;
   const double fused_bytes = lines * N * ((pro && pro->w ? sizeof(T) : 0) + (epi && epi->w ? sizeof(T) : 0) + (epi && epi->acc ? sizeof(cx<T>) : 0));
   ProfScope ps(pname, lines * 2.0 * N * sizeof(cx<T>) + fused_bytes);
-  const long long total = (long long)q.C * (q.tA + q.tB);
-  int rc = call(0, (int)std::min<long long>(resident, total));
+  const long long total = (long long)q.C << (q.lgT + 1);
+  const int grid = (int)std::min<long long>(resident, total);
+  static unsigned long long* dbg_dev = nullptr;
+  const int dbg = env_int("FFB_L2_DEBUG", 0);
+  if (dbg) {
+    if (!dbg_dev) FFB_CUDA(cudaMalloc(&dbg_dev, 6 * sizeof(unsigned long long)));
+    FFB_CUDA(cudaMemsetAsync(dbg_dev, 0, 6 * sizeof(unsigned long long), st));
+    q.dbg = dbg_dev;
+  }
+  int rc = call(0, grid);
+  if (dbg && rc == FFB_OK) {
+    unsigned long long h[6];
+    FFB_CUDA(cudaMemcpyAsync(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost, st));
+    FFB_CUDA(cudaStreamSynchronize(st));
+    const double loop = (double)h[3];
+    fprintf(stderr, "[l2four N=%dx%d dir=%d Wc=%d C=%d D=%d slots=%d grid=%d tA=%d tB=%d] per-CTA mean: loop %.0f cyc, tiles %.1f, wait-slot %.1f%%, wait-A %.1f%%, publish %.1f%%, waits %.1f\n",
+            N1, N2, dir, Wc, q.C, q.D, q.nslots, grid, tiles, tiles, loop / grid, (double)h[4] / grid, 100.0 * h[0] / loop, 100.0 * h[1] / loop, 100.0 * h[2] / loop, (double)h[5] / grid);
+  }
   return rc == 1 ? set_error(FFB_EUNSUPPORTED, "no fused four-step kernel for N = %d x %d", N1, N2) : rc;
 }
 
@@ -920,7 +950,7 @@ int ffb_plan_create(ffb_plan** out, int ndim, const int64_t* n, int dtype, int k
   pl->ndim = ndim; pl->dtype = dtype; pl->kind = kind; pl->nbatch = nbatch; pl->flags = flags;
   pl->dist = nullptr; pl->nyl = pl->nzl = 0; pl->nchunks = 1;
   pl->recv[0] = pl->recv[1] = nullptr; pl->p2p = 0; pl->p2p_cur = 0; pl->recv_bytes = 0;
-  pl->ring = nullptr; pl->ring_bytes = 0; pl->ctr = nullptr; pl->ctr_count = 0;
+  pl->ring = nullptr; pl->ring_bytes = 0; pl->ctr = nullptr; pl->ctr_count = 0; pl->ctr_C = -1;
   for (int b = 0; b < 2; ++b) for (int q = 0; q < 8; ++q) pl->peers[b][q] = nullptr;
   for (int d = 0; d < 3; ++d) { pl->n[d] = d < ndim ? n[d] : 1; pl->nc[d] = pl->n[d]; pl->tables[d] = nullptr; pl->ws[d] = nullptr; }
   if (kind == FFB_R2C) pl->nc[0] = pl->n[0] / 2 + 1;

@@ -6,7 +6,8 @@
 //     in : x[j + k*N/r]                      = register  b + k*R/r      (the same registers in every pass)
 //     out: y[(j/Ns)*Ns*r + (j%Ns) + k*Ns]    -> scattered store to shared memory, then re-read at t + m*N/R
 //   first pass loads global memory at t + m*N/R, last pass lands on the same positions: both coalesced.
-// Exchange words are 8 bytes (Float64: re and im in two phases; Float32: one float2 phase) padded by one word
+// Exchange words are 8 bytes (Float64 rows: re and im in two phases; Float32: one float2 phase; Float64 strided passes move
+// whole 16-byte complex values in one phase) padded by one word
 // every 16, which the design model (tools/fft_model.py) shows to be bank-conflict free for every plan below.
 //
 // Modes (replace the cuFFT/FFTW plans of src/domains.jl:2-5 executed by mul!/ldiv!, src/diffusion.jl:137-139):
@@ -84,16 +85,21 @@ FFB_D int xpad(int i) { return i + (i >> 4); }
 __host__ __device__ constexpr int xpad_len(int n) { return n + (n >> 4) + 1; }
 
 // ---- exchange word access: F64 moves re / im separately, F32 moves the whole float2 ----
-template <typename T> struct xword;
-template <> struct xword<double> { using type = double; static constexpr int phases = 2; };
-template <> struct xword<float> { using type = float2; static constexpr int phases = 1; };
+// ROWS, Float64: 8-byte words in two phases (re, im): the padded layout is bank-conflict free for 8-byte words only.
+// COLS, Float64: whole complex values (16-byte words) in ONE phase: a warp's lanes hold adjacent columns, i.e. contiguous
+// words, which is conflict free for any word size; half the barriers (ncu: the strided Float64 passes stall on barriers).
+template <typename T, bool COLS> struct xword;
+template <> struct xword<double, false> { using type = double; static constexpr int phases = 2; };
+template <> struct xword<double, true> { using type = double2; static constexpr int phases = 1; };
+template <bool COLS> struct xword<float, COLS> { using type = float2; static constexpr int phases = 1; };
 
-template <typename T, int PH> FFB_D typename xword<T>::type xget(const cx<T>& c) {
-  if constexpr (sizeof(T) == 8) return PH == 0 ? c.x : c.y;
+template <typename T, bool COLS, int PH> FFB_D typename xword<T, COLS>::type xget(const cx<T>& c) {
+  if constexpr (sizeof(T) == 8 && !COLS) return PH == 0 ? c.x : c.y;
+  else if constexpr (sizeof(T) == 8) return make_double2(c.x, c.y);
   else return make_float2(c.x, c.y);
 }
-template <typename T, int PH> FFB_D void xput(cx<T>& c, typename xword<T>::type w) {
-  if constexpr (sizeof(T) == 8) { if (PH == 0) c.x = w; else c.y = w; }
+template <typename T, bool COLS, int PH> FFB_D void xput(cx<T>& c, typename xword<T, COLS>::type w) {
+  if constexpr (sizeof(T) == 8 && !COLS) { if (PH == 0) c.x = w; else c.y = w; }
   else { c.x = w.x; c.y = w.y; }
 }
 
@@ -110,7 +116,7 @@ template <int I, int N, typename F> FFB_D void static_for(F&& f) {
 // roofline), so the padded index is split into a per-thread base, computed once, plus compile-time constants: adding a
 // multiple of 16 commutes with xpad, and xpad(16*j + k) = 17*j + k for k < 16.
 template <typename T, bool COLS, int R, int N, int Ns, int r>
-FFB_D void exchange(cx<T> (&v)[R], int t, int w, int W, typename xword<T>::type* xb) {
+FFB_D void exchange(cx<T> (&v)[R], int t, int w, int W, typename xword<T, COLS>::type* xb) {
   constexpr int Tn = N / R, nb = R / r;
   constexpr int lNs = ce_log2(Ns), lr = ce_log2(r);
   constexpr bool kfast = (Ns % 16 == 0) || (Ns == 1 && r == 16);   // k*Ns moves the padded index by a constant
@@ -125,9 +131,11 @@ FFB_D void exchange(cx<T> (&v)[R], int t, int w, int W, typename xword<T>::type*
     sb[b] = (Ns == 1 && r == 16) ? lin(17 * j) : lin(xpad(base));
   }
   const int gb = lin(xpad(t));
-  static_for<0, xword<T>::phases>([&](auto PH) {
+  static_for<0, xword<T, COLS>::phases>([&](auto PH) {
     constexpr int ph = decltype(PH)::value;
-    __syncthreads();  // previous gather finished before the buffer is overwritten
+    // previous gather finished before the buffer is overwritten.  Not needed before the first scatter of a tile (Ns == 1, first
+    // phase): nothing of this tile has touched the buffer yet, and a persistent kernel ends every tile with a barrier.
+    if constexpr (!(Ns == 1 && ph == 0)) __syncthreads();
 #pragma unroll
     for (int b = 0; b < nb; ++b) {
       const int j = t + b * Tn;
@@ -135,14 +143,14 @@ FFB_D void exchange(cx<T> (&v)[R], int t, int w, int W, typename xword<T>::type*
 #pragma unroll
       for (int k = 0; k < r; ++k) {
         const int a = kfast ? sb[b] + step(Ns == 1 ? k : (k * Ns / 16) * 17) : lin(xpad(base + k * Ns));
-        xb[a] = xget<T, ph>(v[b + k * nb]);
+        xb[a] = xget<T, COLS, ph>(v[b + k * nb]);
       }
     }
     __syncthreads();
 #pragma unroll
     for (int m = 0; m < R; ++m) {
       const int a = mfast ? gb + step((m * Tn / 16) * 17) : lin(xpad(t + m * Tn));
-      xput<T, ph>(v[m], xb[a]);
+      xput<T, COLS, ph>(v[m], xb[a]);
     }
   });
 }
@@ -169,7 +177,7 @@ template <typename T, int R, int r, int b> FFB_D void apply_twiddle_powers(cx<T>
 // All passes of one line, recursively over the radix pack.  TWOFF = offset of this pass's base twiddles
 // (tw[TWOFF + a] = exp(-2*pi*i*a/(Ns*r)), a < Ns) in the table.
 template <typename T, int DIR, bool COLS, int R, int N, int Ns, int TWOFF, int r, int... Rest>
-FFB_D void run_passes(cx<T> (&v)[R], int t, int w, int W, typename xword<T>::type* xb, const cx<T>* tw) {
+FFB_D void run_passes(cx<T> (&v)[R], int t, int w, int W, typename xword<T, COLS>::type* xb, const cx<T>* tw) {
   constexpr int Tn = N / R, nb = R / r;
   cx<T> wb[nb];
   if constexpr (Ns > 1) {
@@ -255,15 +263,19 @@ FFB_D cx<T> fuse_factor(T cr, T ci, const T* k0, const T* kt, const T* ko, const
 // grid, pin / pout = array bases (p.in / p.out for the plain launch; the persistent fused four-step kernel of fft_l2four.cuh
 // substitutes its L2-resident scratch ring), nlines = first inactive line.  IN_CG: load the input with ld.global.cg (L2 only):
 // data written by other CTAs of the SAME kernel must not be served from a stale L1 line.
-template <typename T, int DIR, int MODE, bool IN_CG, int R, int... Rs>
+struct NoHook { FFB_D void operator()() const {} };
+
+// after_load() runs once the tile's global loads have been issued (before anything waits for them): the persistent kernel of
+// fft_l2four.cuh publishes the previous tile there, so that the fence it needs overlaps this tile's load latency.
+template <typename T, int DIR, int MODE, bool IN_CG, int R, int... Rs, class AfterLoad = NoHook>
 FFB_D void fft_pow2_tile(const Pow2Params<T>& p, const unsigned bx, const unsigned by, const unsigned gdx, const unsigned gdy, const void* pin,
-                         void* pout, const long long nlines) {
+                         void* pout, const long long nlines, AfterLoad after_load = AfterLoad()) {
   constexpr int N = radix_product<Rs...>::value;
   constexpr int Tn = N / R;
   constexpr bool COLS = (MODE == C2C_COLS || MODE == C2C_COLS_TW || MODE == C2C_COLS_LEAN);
   constexpr bool LEAN = (MODE == C2C_COLS_LEAN);
   static_assert(N % R == 0, "R must divide N");
-  using XW = typename xword<T>::type;
+  using XW = typename xword<T, COLS>::type;
   extern __shared__ __align__(16) unsigned char ffb_smem[];
   XW* xb = reinterpret_cast<XW*>(ffb_smem);
 
@@ -366,6 +378,7 @@ FFB_D void fft_pow2_tile(const Pow2Params<T>& p, const unsigned bx, const unsign
       const int i = t + m * Tn;
       v[m] = active ? ldin<T, IN_CG>(in + (long long)(i & p.in_seg_mask) * p.in_es + (long long)(i >> p.in_seg_shift) * p.in_seg_stride) : mk<T>(0, 0);
     }
+    after_load();
     if (p.pro.on && active) {
       const int i0 = (int)(line % p.pro.n0);
       const long long io = p.pro.other_from_col == 1 ? line / p.pro.n0 : (p.pro.other_from_col == 2 ? (long long)o_lo : o_hi);
@@ -397,14 +410,14 @@ FFB_D void fft_pow2_tile(const Pow2Params<T>& p, const unsigned bx, const unsign
   if constexpr (MODE == R2C_ROWS) {
     // X[k] = 1/2 [ (Z[k] + conj(Z[N-k])) - i*exp(-i*pi*k/N)*(Z[k] - conj(Z[N-k])) ],  k = 0..N
     // Z is staged once in shared memory (Float64: separate re / im planes) so the partner Z[N-k] can be read back.
-    constexpr int PL = xword<T>::phases;
+    constexpr int PL = xword<T, false>::phases;
     const int plane = xpad_len(N) * W;
     auto addr = [&](int idx) { return w * xpad_len(N) + xpad(idx); };
     __syncthreads();
 #pragma unroll
     for (int m = 0; m < R; ++m) {
-      xb[addr(t + m * Tn)] = xget<T, 0>(v[m]);
-      if constexpr (PL == 2) xb[plane + addr(t + m * Tn)] = xget<T, 1>(v[m]);
+      xb[addr(t + m * Tn)] = xget<T, false, 0>(v[m]);
+      if constexpr (PL == 2) xb[plane + addr(t + m * Tn)] = xget<T, false, 1>(v[m]);
     }
     __syncthreads();
     cx<T>* out = reinterpret_cast<cx<T>*>(pout) + o_lo * p.out_os + o_hi * p.out_os2 + line * p.out_ls;
@@ -415,8 +428,8 @@ FFB_D void fft_pow2_tile(const Pow2Params<T>& p, const unsigned bx, const unsign
       const int k = t + m * Tn;
       const int kp = (N - k) & (N - 1);
       cx<T> zp;
-      xput<T, 0>(zp, xb[addr(kp)]);
-      if constexpr (PL == 2) xput<T, 1>(zp, xb[plane + addr(kp)]);
+      xput<T, false, 0>(zp, xb[addr(kp)]);
+      if constexpr (PL == 2) xput<T, false, 1>(zp, xb[plane + addr(kp)]);
       const cx<T> wk = split_twiddle<T, R, N, m>(p.twr, wbase, t);
       const cx<T> s = v[m] + conj(zp), d = v[m] - conj(zp);
       const cx<T> x = half * (s + mul_mi(wk * d));
@@ -515,6 +528,30 @@ FFB_D void fft_pow2_tile(const Pow2Params<T>& p, const unsigned bx, const unsign
   }
 }
 
+// L2 prefetch of the input (and the dense prologue factor) of a strided tile that this CTA will transform next
+template <typename T, int R, int N>
+FFB_D void fft_pow2_prefetch_cols(const Pow2Params<T>& p, const unsigned bx, const unsigned by, const void* pin, const long long nlines) {
+  constexpr int Tn = N / R;
+  const int W = p.W;
+  const int w = threadIdx.x % W, t = threadIdx.x / W;
+  const long long line = (long long)bx * W + w;
+  if (line >= nlines) return;
+  const int o_lo = (int)(by % (unsigned)p.outer_mod);
+  const long long o_hi = by / (unsigned)p.outer_mod;
+  const long long base = o_lo * p.in_os + o_hi * p.in_os2 + line * p.in_ls;
+  const cx<T>* in = reinterpret_cast<const cx<T>*>(pin) + base;
+  // a warp's lanes cover adjacent columns of one row: one prefetch per 128-byte line is enough
+  const bool lead = ((reinterpret_cast<uintptr_t>(in) & 127) < sizeof(cx<T>)) || w == 0;
+  if (!lead) return;
+#pragma unroll
+  for (int m = 0; m < R; ++m) prefetch_l2(in + (long long)(t + m * Tn) * p.in_es);
+  if (p.pro.on && p.pro.w) {
+    const T* wp = p.pro.w + base;
+#pragma unroll
+    for (int m = 0; m < R; ++m) prefetch_l2(wp + (long long)(t + m * Tn) * p.in_es);
+  }
+}
+
 template <typename T, int DIR, int MODE, int MAXT, int MINB, int R, int... Rs>
 __global__ void __launch_bounds__(MAXT, MINB) fft_pow2_kernel(const __grid_constant__ Pow2Params<T> p) {
   const unsigned bx = p.reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
@@ -524,7 +561,8 @@ __global__ void __launch_bounds__(MAXT, MINB) fft_pow2_kernel(const __grid_const
 
 // shared-memory bytes needed by a launch with W lines per CTA (the r2c split step stages full complex values)
 template <typename T> constexpr size_t pow2_smem_bytes(int N, int W, int mode) {
-  return (size_t)xpad_len(N) * W * 8 * ((mode == R2C_ROWS && sizeof(T) == 8) ? 2 : 1);
+  const bool cols = (mode == C2C_COLS || mode == C2C_COLS_TW || mode == C2C_COLS_LEAN);
+  return (size_t)xpad_len(N) * W * 8 * (((mode == R2C_ROWS || cols) && sizeof(T) == 8) ? 2 : 1);
 }
 
 }  // namespace ffb

@@ -12,7 +12,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import fourierflows_jl_b200 as ff  # noqa: E402
 from fourierflows_jl_b200 import _lib as L  # noqa: E402
 
-KEYS = ("FFB_L2FOUR", "FFB_L2_CHUNK", "FFB_L2_AHEAD", "FFB_FOURSTEP_MIN", "FFB_L2_POLICY")
+KEYS = ("FFB_L2FOUR", "FFB_L2_CHUNK", "FFB_L2_AHEAD", "FFB_FOURSTEP_MIN", "FFB_L2_PF", "FFB_L2_ACQ")
 
 
 def time_plan(shape, T, reps=8):
@@ -55,7 +55,9 @@ def main():
     variants = [{"FFB_L2FOUR": "0"}, {}, {"FFB_L2_CHUNK": "2"}, {"FFB_L2_CHUNK": "4"}, {"FFB_L2_AHEAD": "10"}, {"FFB_L2_AHEAD": "40"},
                 {"FFB_FOURSTEP_MIN": "1024"}, {"FFB_FOURSTEP_MIN": "1024", "FFB_L2FOUR": "0"}, {"FFB_FOURSTEP_MIN": "100000"}]
     if quick:
-        cases, variants = cases[:2], variants[:3]
+        cases = cases[:3]
+        variants = [{"FFB_L2FOUR": "0"}, {}, {"FFB_L2_PF": "0"}, {"FFB_L2_ACQ": "0"}, {"FFB_L2_CHUNK": "1"}, {"FFB_L2_CHUNK": "4"},
+                    {"FFB_L2_AHEAD": "10"}, {"FFB_L2_AHEAD": "15"}, {"FFB_L2_AHEAD": "15", "FFB_L2_CHUNK": "4"}]
     for shape, T in cases:
         for v in variants:
             for k in KEYS:
