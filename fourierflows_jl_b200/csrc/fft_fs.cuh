@@ -1,0 +1,200 @@
+// Lean tiles for the two sub-passes of a four-step transform of long strided lines (N = N1*N2, fft_plan.cu:fourstep_min):
+//   A: N1-point transforms over n1 (element stride N2*inner) for fixed n2, output k1 in place of n1, times exp(-/+2 pi i n2 k1/N)
+//   B: N2-point transforms over n2 for fixed k1, output index k1 + N1*k2
+// Used by the stand-alone sub-pass kernels below (one CTA per tile) and by the persistent fused kernel of fft_l2four.cuh
+// (intermediate kept in L2).  Compared with the general strided pass of fft_pow2.cuh (segmented strides, runtime fusion hooks:
+// ~4100 SASS instructions, 128 registers in Float64) these tiles
+//   * get every tile-dependent address from the caller and add compile-time multiples of two strides: ~750 instructions;
+//   * hold R = 8 points per thread in Float64 (32 data registers, <= 80 registers): 24 warps per SM instead of 16 -- the
+//     Float64 passes are latency-bound (ncu: issue slots 37 % busy, barrier / long-scoreboard stalls), not bandwidth-bound;
+//   * compile the calcN! fusion hooks (spectral factor on load, accumulate + dealias on store) in or out (PRO / EPI).
+#pragma once
+#include "fft_pow2.cuh"
+
+namespace ffb {
+
+template <typename T>
+struct FsParams {
+  long long in_es, out_es;     // element (transform index) strides of input / output, in complex elements
+  long long in_ms, out_ms;     // Tn * in_es, Tn * out_es: stride between a thread's consecutive registers
+  int W, lgW;                  // columns per tile (power of two)
+  T scale;                     // applied to the output when != 1
+  const cx<T>* tw;             // base twiddles of this sub-transform (fft_pow2.cuh run_passes)
+  const cx<T>* twN;            // A: exp(-2 pi i q / N), q < N
+  int twN_mask;                // N - 1
+  typename Pow2Params<T>::Fuse hook;   // PRO (A) or EPI (B) operands; .w / .acc are indexed like the true array
+};
+
+struct FsTile {
+  long long in_off, out_off;   // offsets of the tile origin (column line0, transform index 0) in the input / output array
+  long long hook_off;          // the same origin in the TRUE array the hook operands are laid out like (A: input, B: output)
+  long long line0;             // global column index of the tile's first column
+  long long o_hi;              // outer slice index
+  int o_lo;                    // A: n2, B: k1
+  int ncols;                   // active columns of this tile (ragged last tile)
+};
+
+// `sched.before_store()` runs when the transform is done and nothing of this thread is outstanding any more: the persistent fused
+// kernel publishes the previous tile there (a fence at that point returns at once) and looks at the next tile's dependency.
+struct FsNoSched { FFB_D void before_store() const {} };
+
+template <typename T, int DIR, bool IS_A, bool HOOK, bool IN_CG, bool OUT_KEEP, int R, int... Rs, class Sched = FsNoSched>
+FFB_D void fs_tile(const FsParams<T>& p, const cx<T>* pin, cx<T>* pout, const FsTile& tl, Sched sched = Sched()) {
+  constexpr int N = radix_product<Rs...>::value;
+  constexpr int Tn = N / R;
+  static_assert(N % R == 0, "R must divide N");
+  using XW = typename xword<T, true>::type;
+  extern __shared__ __align__(16) unsigned char ffb_smem[];
+  XW* xb = reinterpret_cast<XW*>(ffb_smem);
+  const int W = p.W;
+  const int tid = threadIdx.x;
+  const int w = tid & (W - 1);
+  const int t = tid >> p.lgW;
+  const bool active = w < tl.ncols;
+  cx<T> v[R];
+  // ---------------- load ----------------
+  const cx<T>* in = pin + tl.in_off + w + (long long)t * p.in_es;
+#pragma unroll
+  for (int m = 0; m < R; ++m) v[m] = active ? ldin<T, IN_CG>(in + (long long)m * p.in_ms) : mk<T>(0, 0);
+  if constexpr (HOOK && IS_A) {
+    // prologue: (cr + i ci) * k0[i0] * kt[it] * ko[io] * w[.] * x, evaluated left to right like `im * l * invKrsq * sol`
+    if (active) {
+      const typename Pow2Params<T>::Fuse& h = p.hook;
+      const long long line = tl.line0 + w;
+      const int i0 = (int)(line % h.n0);
+      const long long io = h.other_from_col == 1 ? line / h.n0 : (h.other_from_col == 2 ? (long long)tl.o_lo : tl.o_hi);
+      const T* wp = h.w ? h.w + tl.hook_off + w + (long long)t * p.in_es : nullptr;
+      T wv[R];
+#pragma unroll
+      for (int m = 0; m < R; ++m) wv[m] = wp ? __ldcs(wp + (long long)m * p.in_ms) : T(1);   // independent loads first
+      T fr0 = h.cr, fi0 = h.ci;
+      if (h.k0) { const T q = __ldg(h.k0 + i0); fr0 *= q; fi0 *= q; }
+#pragma unroll
+      for (int m = 0; m < R; ++m) {
+        const int it = h.idm * (t + m * Tn) + h.ido * tl.o_lo;
+        T fr = fr0, fi = fi0;
+        if (h.kt) { const T q = __ldg(h.kt + it); fr *= q; fi *= q; }
+        if (h.ko) { const T q = __ldg(h.ko + io); fr *= q; fi *= q; }
+        if (wp) { fr *= wv[m]; fi *= wv[m]; }
+        v[m] = mk<T>(fr, fi) * v[m];
+      }
+    }
+  }
+  // ---------------- transform ----------------
+  run_passes<T, DIR, true, R, N, 1, 0, Rs...>(v, t, w, W, xb, p.tw);
+  // ---------------- store ----------------
+  if constexpr (IS_A) {
+    // inter-pass twiddle exp(-/+2 pi i n2 k1 / N), k1 = t + m*Tn, n2 = o_lo (the same for every column of the tile)
+    cx<T> wv[R];
+#pragma unroll
+    for (int m = 0; m < R; ++m) wv[m] = load_tw<T, DIR>(p.twN + ((tl.o_lo * (t + m * Tn)) & p.twN_mask));
+#pragma unroll
+    for (int m = 0; m < R; ++m) v[m] = v[m] * wv[m];
+  }
+  sched.before_store();
+  if (!active) return;
+  cx<T>* out = pout + tl.out_off + w + (long long)t * p.out_es;
+  const T sc = p.scale;
+  if constexpr (HOOK && !IS_A) {
+    // epilogue: out = dealias( F * (sc * y) + G * acc ), F = (cr + i ci) k0 kt ko w, G = (ar + i ai) a0 at ao
+    const typename Pow2Params<T>::Fuse& h = p.hook;
+    const long long line = tl.line0 + w;
+    const int i0 = (int)(line % h.n0);
+    const long long io = h.other_from_col == 1 ? line / h.n0 : (h.other_from_col == 2 ? (long long)tl.o_lo : tl.o_hi);
+    const bool dead0 = h.dealias && ((h.lo0 > 0 && i0 >= h.lo0 - 1 && i0 < h.hi0) || (h.loo > 0 && io >= h.loo - 1 && io < h.hio));
+    const long long hb = tl.hook_off + w + (long long)t * p.out_es;
+    cx<T> av[R];
+    bool dead[R];
+#pragma unroll
+    for (int m = 0; m < R; ++m) {   // independent loads of the accumulated array first
+      const int it = h.idm * (t + m * Tn) + h.ido * tl.o_lo;
+      dead[m] = dead0 || (h.dealias && h.lot > 0 && it >= h.lot - 1 && it < h.hit);
+      av[m] = (h.acc && !dead[m]) ? ldc(h.acc + hb + (long long)m * p.out_ms) : mk<T>(0, 0);
+    }
+#pragma unroll
+    for (int m = 0; m < R; ++m) {
+      const int it = h.idm * (t + m * Tn) + h.ido * tl.o_lo;
+      cx<T> r = mk<T>(0, 0);
+      if (!dead[m]) {
+        r = fuse_factor<T>(h.cr, h.ci, h.k0, h.kt, h.ko, h.w, i0, it, io, hb + (long long)m * p.out_ms) * (sc * v[m]);
+        if (h.acc) r = r + fuse_factor<T>(h.ar, h.ai, h.a0, h.at, h.ao, (const T*)nullptr, i0, it, io, 0) * av[m];
+      }
+      stc(out + (long long)m * p.out_ms, r);
+    }
+  } else {
+    if (sc != T(1)) {
+#pragma unroll
+      for (int m = 0; m < R; ++m) stk(out + (long long)m * p.out_ms, sc * v[m], OUT_KEEP ? 1 : 0);
+    } else {
+#pragma unroll
+      for (int m = 0; m < R; ++m) stk(out + (long long)m * p.out_ms, v[m], OUT_KEEP ? 1 : 0);
+    }
+  }
+}
+
+// L2 prefetch of an A tile's input (and dense prologue factor): one request per 128-byte line
+template <typename T, int R, int N>
+FFB_D void fs_prefetch(const FsParams<T>& p, const cx<T>* pin, const FsTile& tl, bool with_w) {
+  constexpr int Tn = N / R;
+  const int w = threadIdx.x & (p.W - 1), t = threadIdx.x >> p.lgW;
+  if (w >= tl.ncols) return;
+  const cx<T>* in = pin + tl.in_off + w + (long long)t * p.in_es;
+  if (!(((reinterpret_cast<uintptr_t>(in) & 127) < sizeof(cx<T>)) || w == 0)) return;
+#pragma unroll
+  for (int m = 0; m < R; ++m) prefetch_l2(in + (long long)m * p.in_ms);
+  if (with_w && p.hook.w) {
+    const T* wp = p.hook.w + tl.hook_off + w + (long long)t * p.in_es;
+#pragma unroll
+    for (int m = 0; m < R; ++m) prefetch_l2(wp + (long long)m * p.in_ms);
+  }
+}
+
+// radix plan of a sub-transform as a type: the fused kernel is a template over two of them
+template <int R_, int... Rs> struct FsPlan {
+  static constexpr int R = R_;
+  static constexpr int N = radix_product<Rs...>::value;
+  template <typename T, int DIR, bool IS_A, bool HOOK, bool IN_CG, bool OUT_KEEP, class Hook>
+  static FFB_D void tile(const FsParams<T>& p, const cx<T>* pin, cx<T>* pout, const FsTile& tl, Hook hook) {
+    fs_tile<T, DIR, IS_A, HOOK, IN_CG, OUT_KEEP, R_, Rs...>(p, pin, pout, tl, hook);
+  }
+  template <typename T>
+  static FFB_D void prefetch(const FsParams<T>& p, const cx<T>* pin, const FsTile& tl, bool with_w) { fs_prefetch<T, R_, N>(p, pin, tl, with_w); }
+};
+
+// Float64: 8 points per thread; Float32: 16 (32 data registers either way)
+template <typename T, int N> struct fs_plan_for;
+template <> struct fs_plan_for<double, 32> { using type = FsPlan<8, 8, 4>; };
+template <> struct fs_plan_for<double, 64> { using type = FsPlan<8, 8, 8>; };
+template <> struct fs_plan_for<double, 128> { using type = FsPlan<8, 8, 8, 2>; };
+template <> struct fs_plan_for<double, 256> { using type = FsPlan<8, 8, 8, 4>; };
+template <> struct fs_plan_for<float, 32> { using type = FsPlan<16, 16, 2>; };
+template <> struct fs_plan_for<float, 64> { using type = FsPlan<16, 16, 4>; };
+template <> struct fs_plan_for<float, 128> { using type = FsPlan<16, 16, 8>; };
+template <> struct fs_plan_for<float, 256> { using type = FsPlan<16, 16, 16>; };
+
+// ---------------------------------------------------------------- stand-alone sub-pass kernels (two-kernel four-step)
+// grid: x = column tile, y = o_lo + mod * o_hi
+template <typename T>
+struct FsLaunch {
+  FsParams<T> p;
+  const cx<T>* in;
+  cx<T>* out;
+  long long in_os, in_os2, out_os, out_os2;   // strides of o_lo / o_hi
+  long long nlines;
+  int mod;                                    // N2 (A) or N1 (B)
+};
+
+template <typename T, int DIR, bool IS_A, bool HOOK, class PL, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) fs_pass_kernel(const __grid_constant__ FsLaunch<T> q) {
+  FsTile tl;
+  tl.o_lo = (int)(blockIdx.y % (unsigned)q.mod);
+  tl.o_hi = blockIdx.y / (unsigned)q.mod;
+  tl.line0 = (long long)blockIdx.x * q.p.W;
+  tl.ncols = (int)min((long long)q.p.W, q.nlines - tl.line0);
+  tl.in_off = tl.o_lo * q.in_os + tl.o_hi * q.in_os2 + tl.line0;
+  tl.out_off = tl.o_lo * q.out_os + tl.o_hi * q.out_os2 + tl.line0;
+  tl.hook_off = IS_A ? tl.in_off : tl.out_off;
+  PL::template tile<T, DIR, IS_A, HOOK, false, false>(q.p, q.in, q.out, tl, FsNoSched());
+}
+
+}  // namespace ffb

@@ -1,7 +1,7 @@
 // Fused four-step transform of long strided lines with the intermediate kept in L2 (sm_100a, 126 MB L2).
 //
 // A strided line of N = N1*N2 points is too long for one CTA to own a wide tile of (fft_plan.cu:fourstep_min), so it is
-// transformed as two short sub-passes: A = N1-point transforms over n1 for fixed n2, times exp(-/+2 pi i n2 k1 / N);
+// transformed as two short sub-passes (tiles: fft_fs.cuh): A = N1-point transforms over n1 for fixed n2, times exp(-/+2 pi i n2 k1 / N);
 // B = N2-point transforms over n2 for fixed k1, landing on k = k1 + N1 k2.  Run as two kernels the intermediate makes a full
 // HBM round trip (a 2-D transform costs P + 5S instead of the P + 3S of SURVEY 8d).  Here ONE persistent kernel runs both
 // sub-passes chunk by chunk: the array is cut into chunks of Wc adjacent columns (x one outer slice); A(c) writes its output
@@ -16,26 +16,16 @@
 // larger ticket, so the schedule cannot deadlock whatever the hardware's CTA placement; with D large enough the waits are
 // already satisfied when they are reached.
 #pragma once
-#include "fft_pow2.cuh"
+#include "fft_fs.cuh"
 
 namespace ffb {
 
-template <int R_, int... Rs> struct RadixPlan {
-  static constexpr int R = R_;
-  static constexpr int N = radix_product<Rs...>::value;
-  template <typename T, int DIR, int MODE, bool IN_CG, class Hook>
-  static FFB_D void tile(const Pow2Params<T>& p, unsigned bx, unsigned by, const void* pin, void* pout, long long nlines, Hook hook) {
-    fft_pow2_tile<T, DIR, MODE, IN_CG, R_, Rs...>(p, bx, by, 1u, 1u, pin, pout, nlines, hook);
-  }
-  template <typename T>
-  static FFB_D void prefetch(const Pow2Params<T>& p, unsigned bx, unsigned by, const void* pin, long long nlines) {
-    fft_pow2_prefetch_cols<T, R_, N>(p, bx, by, pin, nlines);
-  }
-};
-
 template <typename T>
 struct L2FourParams {
-  Pow2Params<T> a, b;      // sub-pass A (C2C_COLS_TW; a.out_* = scratch strides) and B (C2C_COLS; b.in_* = scratch strides)
+  FsParams<T> a, b;        // sub-pass A (a.out_es = scratch stride N2*Wc) and B (b.in_es = scratch stride Wc)
+  const cx<T>* in;         // true input array (read by A)
+  cx<T>* out;              // true output array (written by B); may equal `in`
+  int N;                   // N1 * N2
   cx<T>* ring;             // nslots * slot_elems complex elements
   long long slot_elems;
   int nslots;
@@ -76,13 +66,20 @@ template <typename T> FFB_D L2Tile l2four_decode(const L2FourParams<T>& p, unsig
   return t;
 }
 
-// Publishes a finished tile: release at gpu scope + count (red.release.gpu = MEMBAR.ALL.GPU + REDG; unlike __threadfence() it
-// does not invalidate the SM's L1, which keeps the twiddle tables).  Called by thread 0 from the NEXT tile's after-load hook, so
-// the fence (which waits for this thread's outstanding accesses) overlaps the load latency the warp has to sit out anyway.
-struct L2Publish {
+// Scheduler work of thread 0 inside a tile, run right before the tile's stores (fs_tile: sched.before_store()), when none of the
+// thread's memory accesses is outstanding any more:
+//   * publish the PREVIOUS tile: release at gpu scope + count (red.release.gpu = MEMBAR.ALL.GPU + REDG; unlike __threadfence()
+//     it does not invalidate the SM's L1).  The previous tile's stores were issued a whole tile ago, so the fence returns at once;
+//   * consume the early look at the NEXT tile's dependency (a relaxed load issued at the start of this tile): when the chunk is
+//     already complete the next tile starts without a poll and without the barrier that would follow it.
+struct L2Sched {
   unsigned long long* pending;   // shared-memory slot holding the completion counter's address (0: nothing to publish)
   unsigned long long* acc;       // shared-memory cycle accumulator (measurement aid) or nullptr
-  FFB_D void operator()() const {
+  int* known;                    // &s_known[k] of the next tile's dependency kind, or nullptr
+  int next_c;                    // chunk the next tile depends on
+  unsigned early, want;          // its completion counter as seen at the start of this tile / the complete value
+  int acq;
+  FFB_D void publish() const {
     if (threadIdx.x == 0) {
       unsigned* done = reinterpret_cast<unsigned*>(*pending);
       if (done != nullptr) {
@@ -91,6 +88,13 @@ struct L2Publish {
         if (acc) *acc += (unsigned long long)(clock64() - t0);
       }
       *pending = 0ull;
+    }
+  }
+  FFB_D void before_store() const {
+    publish();
+    if (threadIdx.x == 0 && known != nullptr && early >= want && next_c > *known) {
+      if (acq) asm volatile("fence.acq_rel.gpu;" ::: "memory");
+      *known = next_c;
     }
   }
 };
@@ -119,10 +123,10 @@ FFB_D int l2four_wait(const unsigned* done, int c, unsigned want, int acq) {
   return last;
 }
 
-template <typename T, int DIR, class PA, class PB, int THREADS, int MINB>
+template <typename T, int DIR, class PA, class PB, bool HOOK_A, bool HOOK_B, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) fft_l2four_kernel(const __grid_constant__ L2FourParams<T> p) {
   constexpr int N1 = PA::N, N2 = PB::N;
-  // loop state lives in shared memory: the transform needs every register (Float64: 64 data registers of 128)
+  // loop state lives in shared memory: the transform needs the registers
   __shared__ unsigned s_tk[4];   // ring of drawn tickets: tile i uses s_tk[i & 3]; tickets are drawn two tiles ahead
   __shared__ int s_known[2];     // [0]: A chunks <= this are complete, [1]: B chunks (a CTA meets its waits in increasing chunk order)
   __shared__ unsigned long long s_pending;   // completion counter of the tile whose stores are issued but not yet published
@@ -140,36 +144,64 @@ __global__ void __launch_bounds__(THREADS, MINB) fft_l2four_kernel(const __grid_
     s_known[0] = -1; s_known[1] = -1; s_pending = 0ull;
   }
   __syncthreads();
+  // tile geometry of a ticket: chunk -> (column chunk cc, outer slice oc); tile index -> (column tile j, o_lo)
+  auto geometry = [&](const L2Tile& t, FsTile& tl, long long& col0) {
+    const unsigned oc = p.ncc == p.C ? 0u : (unsigned)t.c / (unsigned)p.ncc;
+    const unsigned cc = (unsigned)t.c - oc * (unsigned)p.ncc;
+    col0 = (long long)cc * p.Wc;
+    const int lg = t.isB ? p.lg_tcb : p.lg_tca, lgW = t.isB ? p.lgWB : p.lgWA;
+    const unsigned j = (unsigned)t.idx & ((1u << lg) - 1u);
+    tl.o_lo = (int)((unsigned)t.idx >> lg);
+    tl.o_hi = oc;
+    const long long loc = (long long)j << lgW;            // first column of the tile inside the chunk
+    tl.line0 = col0 + loc;
+    tl.ncols = (int)max(0ll, min((long long)(1 << lgW), p.inner - tl.line0));
+    const long long slot = (long long)((unsigned)t.c % (unsigned)p.nslots) * p.slot_elems;
+    const long long arr = (long long)tl.o_lo * p.inner + (long long)oc * p.inner * p.N + tl.line0;   // o_lo = n2 (A, input) / k1 (B, output)
+    if (!t.isB) { tl.in_off = arr; tl.out_off = slot + (long long)tl.o_lo * p.Wc + loc; }
+    else { tl.in_off = slot + (long long)tl.o_lo * N2 * p.Wc + loc; tl.out_off = arr; }
+    tl.hook_off = arr;
+  };
   for (unsigned it = 0;; ++it) {
     const unsigned tk = s_tk[it & 3];
     if (tk >= total) break;
     unsigned drawn = 0;
     if (tid == 0) drawn = atomicAdd(p.ctr, 1u);   // ticket of tile it + 2: consumed (stored) only after this tile's work
     const L2Tile t = l2four_decode(p, tk);
-    const unsigned oc = p.ncc == p.C ? 0u : (unsigned)t.c / (unsigned)p.ncc;
-    const unsigned cc = (unsigned)t.c - oc * (unsigned)p.ncc;
-    const long long col0 = (long long)cc * p.Wc;
-    const long long nl = min(col0 + (long long)p.Wc, p.inner);
-    // scratch addressing uses the tile function's global line index: fold the chunk origin into the base pointer
-    cx<T>* sbase = p.ring + (long long)((unsigned)t.c % (unsigned)p.nslots) * p.slot_elems - col0;
+    FsTile tl;
+    long long col0;
+    geometry(t, tl, col0);
     // the tile after this one: pull its input towards L2 now (A tiles read HBM; B tiles read the ring, already in L2)
     if (p.pf) {
       const unsigned tk1 = s_tk[(it + 1) & 3];
       if (tk1 < total) {
         const L2Tile u = l2four_decode(p, tk1);
         if (!u.isB) {
-          const unsigned uo = p.ncc == p.C ? 0u : (unsigned)u.c / (unsigned)p.ncc;
-          const long long c0 = (long long)((unsigned)u.c - uo * (unsigned)p.ncc) * p.Wc;
-          PA::template prefetch<T>(p.a, (unsigned)(c0 >> p.lgWA) + ((unsigned)u.idx & ((1u << p.lg_tca) - 1u)), ((unsigned)u.idx >> p.lg_tca) + (unsigned)N2 * uo,
-                                   p.a.in, min(c0 + (long long)p.Wc, p.inner));
+          FsTile ul;
+          long long c0;
+          geometry(u, ul, c0);
+          PA::template prefetch<T>(p.a, p.in, ul, HOOK_A);
         }
       }
     }
-    const L2Publish publish{&s_pending, dbg ? &s_dbg[2] : nullptr};
+    // early look at the next tile's dependency: one relaxed load now, consumed before this tile's stores
+    L2Sched sched{&s_pending, dbg ? &s_dbg[2] : nullptr, nullptr, 0, 0u, want, p.acq};
+    {
+      const unsigned tk1 = s_tk[(it + 1) & 3];
+      if (tk1 < total) {
+        const L2Tile u = l2four_decode(p, tk1);
+        const int dep = u.isB ? u.c : u.c - p.nslots;
+        if (dep >= 0) {
+          sched.known = &s_known[u.isB ? 0 : 1];
+          sched.next_c = dep;
+          if (tid == 0) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(sched.early) : "l"((u.isB ? doneA : doneB) + dep) : "memory");
+        }
+      }
+    }
     if (!t.isB) {
       const int need = t.c - p.nslots;   // slot reuse: B(need) must have read the slot
       if (need > s_known[1]) {
-        publish();   // a blocked CTA must have published everything it finished (its own tile may be what others wait for)
+        sched.publish();   // a blocked CTA must have published everything it finished (its own tile may be what others wait for)
         int upto = need;
         if (tid == 0) {
           const long long t0 = dbg ? clock64() : 0;
@@ -179,12 +211,11 @@ __global__ void __launch_bounds__(THREADS, MINB) fft_l2four_kernel(const __grid_
         __syncthreads();
         if (tid == 0) s_known[1] = upto;
       }
-      const unsigned j = (unsigned)t.idx & ((1u << p.lg_tca) - 1u), n2 = (unsigned)t.idx >> p.lg_tca;
-      PA::template tile<T, DIR, C2C_COLS_TW, false>(p.a, (unsigned)(col0 >> p.lgWA) + j, n2 + (unsigned)N2 * oc, p.a.in, sbase, nl, publish);
+      PA::template tile<T, DIR, true, HOOK_A, false, true>(p.a, p.in, p.ring, tl, sched);
       if (tid == 0) s_pending = (unsigned long long)(doneA + t.c);
     } else {
       if (t.c > s_known[0]) {
-        publish();
+        sched.publish();
         int upto = t.c;
         if (tid == 0) {
           const long long t0 = dbg ? clock64() : 0;
@@ -194,14 +225,13 @@ __global__ void __launch_bounds__(THREADS, MINB) fft_l2four_kernel(const __grid_
         __syncthreads();
         if (tid == 0) s_known[0] = upto;
       }
-      const unsigned j = (unsigned)t.idx & ((1u << p.lg_tcb) - 1u), k1 = (unsigned)t.idx >> p.lg_tcb;
-      PB::template tile<T, DIR, C2C_COLS, true>(p.b, (unsigned)(col0 >> p.lgWB) + j, k1 + (unsigned)N1 * oc, sbase, p.b.out, nl, publish);
+      PB::template tile<T, DIR, false, HOOK_B, true, false>(p.b, p.ring, p.out, tl, sched);
       if (tid == 0) s_pending = (unsigned long long)(doneB + t.c);
     }
     if (tid == 0) { s_tk[(it + 2) & 3] = drawn; if (dbg) s_dbg[4] += 1; }
     __syncthreads();   // A: every thread's scratch stores are issued; B: every thread's scratch loads have been consumed; s_tk / s_known visible
   }
-  L2Publish{&s_pending, nullptr}();
+  L2Sched{&s_pending, nullptr, nullptr, 0, 0u, 0u, 0}.publish();
   if (dbg && tid == 0) {
     s_dbg[3] = (unsigned long long)(clock64() - t_begin);
     for (int i = 0; i < 6; ++i) atomicAdd(p.dbg + i, s_dbg[i]);

@@ -59,6 +59,7 @@ struct DimTables {
   int N = 0;             // complex transform length
   bool pow2 = false;     // register-resident kernel available
   cx<T>* tw = nullptr;   // pow2 per-pass twiddles
+  cx<T>* tw8 = nullptr;  // Float64 row passes with 8 points per thread: twiddles of the radix-8 plan (dim 0 only)
   cx<T>* wN = nullptr;   // generic: exp(-2 pi i q / N), q < N
   cx<T>* twr = nullptr;  // split step: exp(-i pi k / N), k <= N (dim 0 of R2C plans only)
   // four-step split of a long strided line: N = N1*N2, two short sub-passes with wide rows
@@ -97,11 +98,9 @@ struct ffb_plan {
 
 namespace ffb {
 
-// base twiddles of the register-resident plan for length N: for each pass with Ns > 1, exp(-2 pi i a/(Ns r)), a < Ns
+// base twiddles of a Stockham plan with the given radix sequence: for each pass with Ns > 1, exp(-2 pi i a/(Ns r)), a < Ns
 template <typename T>
-static int build_pow2_tw(int N, cx<T>** dev) {
-  int rad[8];
-  const int np = pow2_radices(N, rad);
+static int build_tw_radices(const int* rad, int np, cx<T>** dev) {
   std::vector<cx<T>> h;
   int Ns = 1;
   for (int i = 0; i < np; ++i) {
@@ -112,6 +111,32 @@ static int build_pow2_tw(int N, cx<T>** dev) {
   }
   if (h.empty()) h.push_back(mk<T>(1, 0));
   return upload(h, dev);
+}
+// register-resident plan for length N (radix sequence of fft_pow2_dispatch.h)
+template <typename T>
+static int build_pow2_tw(int N, cx<T>** dev) {
+  int rad[8];
+  const int np = pow2_radices(N, rad);
+  return build_tw_radices<T>(rad, np, dev);
+}
+// four-step sub-transform of length N (radix sequence of fft_fs.cuh: 8 points per thread in Float64, 16 in Float32)
+template <typename T>
+static int build_fs_tw(int N, cx<T>** dev) {
+  int rad[8];
+  const int np = fs_radices(N, (int)sizeof(T), rad);
+  if (np == 0) return set_error(FFB_EUNSUPPORTED, "no four-step sub-transform of length %d", N);
+  return build_tw_radices<T>(rad, np, dev);
+}
+
+// Float64 row passes (dim 0) of 512 .. 4096 points have a second plan with 8 points per thread (64 registers, two 512-thread
+// CTAs = 32 warps per SM instead of 16: the row kernels are latency-bound).  pow2_pass finds it through the table of the
+// 16-point plan it is handed.  FFB_ROWS_R8=0 disables.
+static std::mutex g_tw8_mu;
+static std::map<const void*, const void*> g_tw8;
+static const void* rows_tw8_for(const void* tw) {
+  std::lock_guard<std::mutex> lk(g_tw8_mu);
+  auto it = g_tw8.find(tw);
+  return it == g_tw8.end() ? nullptr : it->second;
 }
 
 // Strided lines at least this long are transformed as a four-step pair of short sub-passes (measured: one register-resident
@@ -140,9 +165,9 @@ static int build_tables(ffb_plan* pl) {
       tb->N1 = 1 << (l2 / 2);
       tb->N2 = N / tb->N1;
       tb->pow2 = true;
-      int rc = build_pow2_tw<T>(tb->N1, &tb->tw1);
+      int rc = build_fs_tw<T>(tb->N1, &tb->tw1);
       if (rc) return rc;
-      if ((rc = build_pow2_tw<T>(tb->N2, &tb->tw2))) return rc;
+      if ((rc = build_fs_tw<T>(tb->N2, &tb->tw2))) return rc;
       std::vector<cx<T>> h((size_t)N);
       for (int q = 0; q < N; ++q) h[q] = unit_root<T>(q, N);
       if ((rc = upload(h, &tb->twN))) return rc;
@@ -156,6 +181,16 @@ static int build_tables(ffb_plan* pl) {
       if (N == 0) h[0] = mk<T>(1, 0);
       int rc = upload(h, &tb->wN);
       if (rc) return rc;
+    }
+    if (d == 0 && sizeof(T) == 8 && tb->pow2 && tb->tw) {
+      int r8[8];
+      const int n8 = pow2_radices_r8(N, r8);
+      if (n8 > 0) {
+        int rc = build_tw_radices<T>(r8, n8, &tb->tw8);
+        if (rc) return rc;
+        std::lock_guard<std::mutex> lk(g_tw8_mu);
+        g_tw8[tb->tw] = tb->tw8;
+      }
     }
     if (split) {
       std::vector<cx<T>> h((size_t)N + 1);
@@ -176,6 +211,8 @@ static void free_tables(ffb_plan* pl) {
   for (int d = 0; d < pl->ndim; ++d) {
     auto* tb = reinterpret_cast<DimTables<T>*>(pl->tables[d]);
     if (!tb) continue;
+    if (tb->tw8) { std::lock_guard<std::mutex> lk(g_tw8_mu); g_tw8.erase(tb->tw); }
+    cudaFree(tb->tw8);
     cudaFree(tb->tw); cudaFree(tb->wN); cudaFree(tb->twr); cudaFree(tb->tw1); cudaFree(tb->tw2); cudaFree(tb->twN);
     delete tb;
   }
@@ -191,9 +228,13 @@ static int ensure_ws(ffb_plan* pl, int count) {
 }
 
 template <typename T>
-static int call_pow2(int N, int mode, int dir, const Pow2Params<T>& p, int gx, int gy, int threads, size_t smem, cudaStream_t st) {
+static int call_pow2(int N, int mode, int dir, const Pow2Params<T>& p, int gx, int gy, int threads, size_t smem, cudaStream_t st, bool r8 = false) {
   int rc;
   if constexpr (sizeof(T) == 8) {
+    if (r8) {
+      if ((rc = pow2_launch_double_r8(N, mode, dir, &p, gx, gy, threads, smem, st)) != 1) return rc;
+      return set_error(FFB_EUNSUPPORTED, "no 8-point-per-thread row kernel for N=%d", N);
+    }
     if ((rc = pow2_launch_double_g0(N, mode, dir, &p, gx, gy, threads, smem, st)) != 1) return rc;
     if ((rc = pow2_launch_double_g1(N, mode, dir, &p, gx, gy, threads, smem, st)) != 1) return rc;
     if ((rc = pow2_launch_double_g2(N, mode, dir, &p, gx, gy, threads, smem, st)) != 1) return rc;
@@ -205,6 +246,11 @@ static int call_pow2(int N, int mode, int dir, const Pow2Params<T>& p, int gx, i
     if ((rc = pow2_launch_float_g3(N, mode, dir, &p, gx, gy, threads, smem, st)) != 1) return rc;
   }
   return set_error(FFB_EUNSUPPORTED, "no register-resident FFT kernel for N=%d", N);
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
 }
 
 // Lines-per-CTA choice (measured: tools/sweep_w.py, tools/sweep2.py, profiles/r01_sweep_*.log).  Throughput is set by how
@@ -302,7 +348,11 @@ static int pow2_pass(int N, int mode, int dir, const void* in, void* out, long l
   p.scale = scale;
   p.tw = tw;
   p.twr = twr;
-  const int R = pow2_points_per_thread(N);
+  int R = pow2_points_per_thread(N);
+  bool r8 = false;
+  if (sizeof(T) == 8 && (mode == C2C_ROWS || mode == R2C_ROWS || mode == C2R_ROWS) && p.W == 1 && env_int("FFB_ROWS_R8", 1)) {
+    if (const void* t8 = rows_tw8_for(tw)) { p.tw = reinterpret_cast<const cx<T>*>(t8); R = 8; r8 = true; }
+  }
   const int threads = (N / R) * p.W;
   if (mode == C2C_COLS_LEAN && p.pf_ahead < 0) p.pf_ahead = threads >= pow2_max_threads(sizeof(T)) ? num_sms() : 0;
   const size_t smem = pow2_smem_bytes<T>(N, p.W, mode);
@@ -330,7 +380,7 @@ static int pow2_pass(int N, int mode, int dir, const void* in, void* out, long l
       if (pro && pro->w) p.pro.w = pro->w + h0 * o2.in_os2;
       if (epi && epi->w) p.epi.w = epi->w + h0 * o2.out_os2;
       if (epi && epi->acc) p.epi.acc = epi->acc + h0 * o2.out_os2;
-      int rc = call_pow2<T>(N, mode, dir, p, (int)gx, (int)(cnt * o2.mod), threads, smem, st);
+      int rc = call_pow2<T>(N, mode, dir, p, (int)gx, (int)(cnt * o2.mod), threads, smem, st, r8);
       if (rc) return rc;
     }
     return FFB_OK;
@@ -349,7 +399,7 @@ static int pow2_pass(int N, int mode, int dir, const void* in, void* out, long l
     if (epi && epi->acc) p.epi.acc = epi->acc + o0 * out_os;
     if (pro || epi) FFB_REQUIRE(nouter <= 65535 || (!(pro && pro->ko) && !(epi && (epi->ko || epi->ao || epi->loo > 0))), FFB_EUNSUPPORTED,
                                 "fused pass with more than 65535 outer slices");
-    int rc = call_pow2<T>(N, mode, dir, p, (int)gx, (int)cnt, threads, smem, st);
+    int rc = call_pow2<T>(N, mode, dir, p, (int)gx, (int)cnt, threads, smem, st, r8);
     if (rc) return rc;
   }
   return FFB_OK;
@@ -384,40 +434,104 @@ static int lean_tile_pass(int N, int dir, int W, const cx<T>* in, long long in_t
   return call_pow2<T>(N, C2C_COLS_LEAN, dir, p, (int)gx, (int)nouter, threads, smem, st);
 }
 
-static int env_int(const char* name, int dflt) {
-  const char* e = getenv(name);
-  return e ? atoi(e) : dflt;
-}
 
 // Fused four-step pass (fft_l2four.cuh): both sub-passes in ONE persistent kernel, intermediate in an L2-resident scratch ring.
-// FFB_L2FOUR=0 falls back to the two-kernel form; FFB_L2_CHUNK = chunk width in units of the wider tile (default 1);
+// Opt-in (FFB_L2FOUR=1): measured slower than the two-kernel form on B200 although it halves the DRAM traffic; FFB_L2_CHUNK = chunk width in units of the wider tile (default 1);
 // FFB_L2_AHEAD = tiles of lookahead of A over B in units of 0.1 x resident CTAs (default 20).
-static bool l2four_enabled(int N1, int N2) { return l2four_has(N1, N2) && env_int("FFB_L2FOUR", 1) != 0; }
+static bool l2four_enabled(int N1, int N2) { return l2four_has(N1, N2) && env_int("FFB_L2FOUR", 0) != 0; }
+
+template <typename T>
+static void fs_params(FsParams<T>& p, int Nsub, long long in_es, long long out_es, T scale, const cx<T>* tw) {
+  const int R = fs_points_per_thread((int)sizeof(T)), Tn = Nsub / R;
+  memset(&p, 0, sizeof(p));
+  p.in_es = in_es; p.out_es = out_es; p.in_ms = (long long)Tn * in_es; p.out_ms = (long long)Tn * out_es;
+  p.W = kFsThreads / Tn; p.lgW = ilog2((uint64_t)p.W);
+  p.scale = scale; p.tw = tw; p.twN = nullptr; p.twN_mask = 0;
+  p.hook.on = 0;
+}
+
+// Stand-alone four-step sub-pass (two-kernel form; the fused form is l2four_pass).  part 1 = A, part 2 = B.
+template <typename T>
+static int fs_pass(const DimTables<T>* tb, int part, long long inner, long long outer, const cx<T>* src, cx<T>* dst, int dir, T scale,
+                   cudaStream_t st, typename Pow2Params<T>::Fuse* pro, typename Pow2Params<T>::Fuse* epi) {
+  const int N = tb->N, N1 = tb->N1, N2 = tb->N2;
+  const bool is_a = part == 1;
+  FsLaunch<T> q;
+  memset(&q, 0, sizeof(q));
+  if (is_a) {
+    fs_params<T>(q.p, N1, (long long)N2 * inner, (long long)N2 * inner, T(1), tb->tw1);
+    q.p.twN = tb->twN; q.p.twN_mask = N - 1;
+    q.in_os = inner; q.out_os = inner; q.mod = N2;
+    FFB_REQUIRE(!epi, FFB_EINVAL, "internal: epilogue on the first four-step sub-pass");
+    if (pro) { pro->idm = N2; pro->ido = 1; q.p.hook = *pro; }
+  } else {
+    fs_params<T>(q.p, N2, inner, (long long)N1 * inner, scale, tb->tw2);
+    q.in_os = (long long)N2 * inner; q.out_os = inner; q.mod = N1;
+    FFB_REQUIRE(!pro, FFB_EINVAL, "internal: prologue on the second four-step sub-pass");
+    if (epi) { epi->idm = N1; epi->ido = 1; q.p.hook = *epi; }
+  }
+  q.in_os2 = inner * N; q.out_os2 = inner * N; q.nlines = inner;
+  const int hook = is_a ? (pro ? 1 : 0) : (epi ? 2 : 0);
+  const int Nsub = is_a ? N1 : N2;
+  const size_t smem = pow2_smem_bytes<T>(Nsub, q.p.W, C2C_COLS);
+  const long long gx = (inner + q.p.W - 1) / q.p.W;
+  FFB_REQUIRE(gx < (1ll << 31) && q.mod <= 65535, FFB_EUNSUPPORTED, "too many lines for one launch");
+  char pname[64];
+  snprintf(pname, sizeof(pname), "fft_fs_%s_%s_N%d", is_a ? "a" : "b", sizeof(T) == 8 ? "f64" : "f32", Nsub);
+  const double lines = (double)inner * (double)outer;
+  const typename Pow2Params<T>::Fuse* h = is_a ? pro : epi;
+  const double fused_bytes = lines * N * ((h && h->w ? sizeof(T) : 0) + (h && h->acc ? sizeof(cx<T>) : 0));
+  ProfScope ps(pname, lines * 2.0 * N * sizeof(cx<T>) + fused_bytes);
+  const long long hchunk = std::max<long long>(1, 65535 / q.mod);
+  FFB_REQUIRE(outer <= hchunk || !(h && (h->ko || h->ao || h->loo > 0)), FFB_EUNSUPPORTED, "fused pass with more than 65535 outer slices");
+  for (long long h0 = 0; h0 < outer; h0 += hchunk) {
+    const long long cnt = std::min<long long>(hchunk, outer - h0);
+    q.in = src + h0 * q.in_os2; q.out = dst + h0 * q.out_os2;
+    if (h && h->w) q.p.hook.w = h->w + h0 * q.in_os2;
+    if (h && h->acc) q.p.hook.acc = h->acc + h0 * q.out_os2;
+    int rc = sizeof(T) == 8 ? fs_call_double(is_a, Nsub, dir, hook, &q, (int)gx, (int)(cnt * q.mod), smem, st)
+                            : fs_call_float(is_a, Nsub, dir, hook, &q, (int)gx, (int)(cnt * q.mod), smem, st);
+    if (rc == 1) return set_error(FFB_EUNSUPPORTED, "no four-step sub-pass kernel for N = %d", Nsub);
+    if (rc) return rc;
+  }
+  return FFB_OK;
+}
 
 template <typename T>
 static int l2four_pass(ffb_plan* pl, const DimTables<T>* tb, long long inner, long long outer, const cx<T>* src, cx<T>* dst, int dir, T scale,
                        cudaStream_t st, typename Pow2Params<T>::Fuse* pro, typename Pow2Params<T>::Fuse* epi) {
   const int N = tb->N, N1 = tb->N1, N2 = tb->N2;
-  const int WA = kL2FourThreads / (N1 / 16), WB = kL2FourThreads / (N2 / 16), Wmax = std::max(WA, WB);
   L2FourParams<T> q;
   memset(&q, 0, sizeof(q));
+  fs_params<T>(q.a, N1, (long long)N2 * inner, 0, T(1), tb->tw1);
+  fs_params<T>(q.b, N2, 0, (long long)N1 * inner, scale, tb->tw2);
+  const int WA = q.a.W, WB = q.b.W, Wmax = std::max(WA, WB);
   int Wc = Wmax * std::max(1, env_int("FFB_L2_CHUNK", 2));
   FFB_REQUIRE(is_pow2((uint64_t)Wc), FFB_EINVAL, "FFB_L2_CHUNK must be a power of two");
   while (Wc > Wmax && Wc / 2 >= inner) Wc /= 2;
+  // scratch chunk layout [N][Wc]: A writes k1 in place of n1 (stride N2*Wc), B reads n2 (stride Wc)
+  q.a.out_es = (long long)N2 * Wc; q.a.out_ms = (long long)(N1 / fs_points_per_thread((int)sizeof(T))) * q.a.out_es;
+  q.b.in_es = Wc; q.b.in_ms = (long long)(N2 / fs_points_per_thread((int)sizeof(T))) * q.b.in_es;
+  q.a.twN = tb->twN; q.a.twN_mask = N - 1;
+  if (pro) { pro->idm = N2; pro->ido = 1; q.a.hook = *pro; }
+  if (epi) { epi->idm = N1; epi->ido = 1; q.b.hook = *epi; }
+  FFB_REQUIRE(!(pro && epi), FFB_EINVAL, "internal: prologue and epilogue on one transform");
+  const int hook = pro ? 1 : (epi ? 2 : 0);
+  q.in = src; q.out = dst; q.N = N;
   q.Wc = Wc; q.inner = inner;
   q.ncc = (int)((inner + Wc - 1) / Wc);
   FFB_REQUIRE((long long)q.ncc * outer < (1ll << 22), FFB_EUNSUPPORTED, "too many chunks for the fused four-step pass");
   q.C = (int)(q.ncc * outer);
   q.Cpad = (q.C + 3) / 4 * 4;
-  q.lgWA = ilog2((uint64_t)WA); q.lgWB = ilog2((uint64_t)WB);
+  q.lgWA = q.a.lgW; q.lgWB = q.b.lgW;
   q.lg_tca = ilog2((uint64_t)(Wc / WA)); q.lg_tcb = ilog2((uint64_t)(Wc / WB));
   const int tiles = (Wc / WA) * N2;   // == (Wc / WB) * N1
   q.lgT = ilog2((uint64_t)tiles);
   FFB_REQUIRE((1 << q.lgT) == tiles && (Wc / WB) * N1 == tiles, FFB_EUNSUPPORTED, "internal: tile counts of the two sub-passes differ");
   FFB_REQUIRE(((long long)q.C << (q.lgT + 1)) < (1ll << 31), FFB_EUNSUPPORTED, "too many tiles for the fused four-step pass");
-  const size_t smem = std::max(pow2_smem_bytes<T>(N1, WA, C2C_COLS_TW), pow2_smem_bytes<T>(N2, WB, C2C_COLS));
+  const size_t smem = std::max(pow2_smem_bytes<T>(N1, WA, C2C_COLS), pow2_smem_bytes<T>(N2, WB, C2C_COLS));
   auto call = [&](int op, int grid) {
-    return sizeof(T) == 8 ? l2four_call_double(op, N1, N2, dir, &q, grid, smem, st) : l2four_call_float(op, N1, N2, dir, &q, grid, smem, st);
+    return sizeof(T) == 8 ? l2four_call_double(op, N1, N2, dir, hook, &q, grid, smem, st) : l2four_call_float(op, N1, N2, dir, hook, &q, grid, smem, st);
   };
   const int per_sm = call(1, 0);
   FFB_REQUIRE(per_sm >= 1, per_sm < 0 ? per_sm : FFB_EUNSUPPORTED, "fused four-step kernel does not fit an SM (N = %d x %d)", N1, N2);
@@ -445,6 +559,7 @@ static int l2four_pass(ffb_plan* pl, const DimTables<T>* tb, long long inner, lo
     int rc = ffb_malloc(&c, nctr * sizeof(unsigned));
     if (rc) return rc;
     pl->ctr = reinterpret_cast<unsigned*>(c); pl->ctr_count = nctr;
+    pl->ctr_C = -1;
   }
   if (pl->ctr_C != q.Cpad) {
     // counter layout depends on the chunk count: start from zero (afterwards every launch leaves the counters zeroed)
@@ -453,27 +568,8 @@ static int l2four_pass(ffb_plan* pl, const DimTables<T>* tb, long long inner, lo
   }
   q.ring = reinterpret_cast<cx<T>*>(pl->ring);
   q.ctr = pl->ctr;
-  q.pf = env_int("FFB_L2_PF", 1);
+  q.pf = env_int("FFB_L2_PF", 0);
   q.acq = env_int("FFB_L2_ACQ", 1);
-  auto base = [&](Pow2Params<T>& p) {
-    p.pro.on = 0; p.epi.on = 0; p.rmul = nullptr; p.reverse = 0; p.pf_ahead = 0;
-    p.in_seg_mask = p.out_seg_mask = 0x7fffffff; p.in_seg_shift = p.out_seg_shift = 31; p.in_seg_stride = p.out_seg_stride = 0;
-    p.in_ls = p.out_ls = 1; p.nlines = inner; p.twr = nullptr; p.twN = nullptr; p.twN_mask = 0;
-  };
-  // A: N1-point transforms over n1 (stride N2*inner) for each n2 = o_lo, output k1 in place of n1, into the scratch chunk [N][Wc]
-  base(q.a);
-  q.a.in = src; q.a.out = nullptr;
-  q.a.in_es = (long long)N2 * inner; q.a.in_os = inner; q.a.in_os2 = inner * N;
-  q.a.out_es = (long long)N2 * Wc; q.a.out_os = Wc; q.a.out_os2 = 0;
-  q.a.outer_mod = N2; q.a.W = WA; q.a.scale = T(1); q.a.tw = tb->tw1; q.a.twN = tb->twN; q.a.twN_mask = N - 1; q.a.keep_out = 1;
-  if (pro) { pro->idm = N2; pro->ido = 1; q.a.pro = *pro; }
-  // B: N2-point transforms over n2 (scratch stride Wc) for each k1 = o_lo (scratch stride N2*Wc), output index k1 + N1*k2
-  base(q.b);
-  q.b.in = nullptr; q.b.out = dst;
-  q.b.in_es = Wc; q.b.in_os = (long long)N2 * Wc; q.b.in_os2 = 0;
-  q.b.out_es = (long long)N1 * inner; q.b.out_os = inner; q.b.out_os2 = inner * N;
-  q.b.outer_mod = N1; q.b.W = WB; q.b.scale = scale; q.b.tw = tb->tw2; q.b.keep_out = 0;
-  if (epi) { epi->idm = N1; epi->ido = 1; q.b.epi = *epi; }
   char pname[64];
   snprintf(pname, sizeof(pname), "fft_l2four_%s_N%d", sizeof(T) == 8 ? "f64" : "f32", N);
   const double lines = (double)inner * (double)outer;
@@ -494,8 +590,8 @@ static int l2four_pass(ffb_plan* pl, const DimTables<T>* tb, long long inner, lo
     FFB_CUDA(cudaMemcpyAsync(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost, st));
     FFB_CUDA(cudaStreamSynchronize(st));
     const double loop = (double)h[3];
-    fprintf(stderr, "[l2four N=%dx%d dir=%d Wc=%d C=%d D=%d slots=%d grid=%d tA=%d tB=%d] per-CTA mean: loop %.0f cyc, tiles %.1f, wait-slot %.1f%%, wait-A %.1f%%, publish %.1f%%, waits %.1f\n",
-            N1, N2, dir, Wc, q.C, q.D, q.nslots, grid, tiles, tiles, loop / grid, (double)h[4] / grid, 100.0 * h[0] / loop, 100.0 * h[1] / loop, 100.0 * h[2] / loop, (double)h[5] / grid);
+    fprintf(stderr, "[l2four N=%dx%d dir=%d Wc=%d C=%d D=%d slots=%d grid=%d tiles/chunk=%d] per-CTA mean: loop %.0f cyc, tiles %.1f, wait-slot %.1f%%, wait-A %.1f%%, publish %.1f%%, waits %.1f\n",
+            N1, N2, dir, Wc, q.C, q.D, q.nslots, grid, tiles, loop / grid, (double)h[4] / grid, 100.0 * h[0] / loop, 100.0 * h[1] / loop, 100.0 * h[2] / loop, (double)h[5] / grid);
   }
   return rc == 1 ? set_error(FFB_EUNSUPPORTED, "no fused four-step kernel for N = %d x %d", N1, N2) : rc;
 }
@@ -514,22 +610,7 @@ static int cols_pass(ffb_plan* pl, const DimTables<T>* tb, int part, long long i
     return pow2_pass<T>(N, C2C_COLS, dir, src, dst, inner, 1, inner * N, inner, 1, inner * N, inner, outer, scale, tb->tw, nullptr, st,
                         SegStride(), SegStride(), Outer2(), nullptr, 0, pro, epi);
   }
-  const int N1 = tb->N1, N2 = tb->N2;
-  Outer2 o2;
-  o2.nhi = outer; o2.in_os2 = inner * N; o2.out_os2 = inner * N;
-  if (part == 1) {  // length-N1 transforms over n1 (element stride N2*inner) for each n2, times exp(-/+2 pi i n2 k1/N)
-    o2.mod = N2;
-    if (pro) { pro->idm = N2; pro->ido = 1; }   // input index n = N2*n1 + n2
-    FFB_REQUIRE(!epi, FFB_EINVAL, "internal: epilogue on the first four-step sub-pass");
-    return pow2_pass<T>(N1, C2C_COLS_TW, dir, src, dst, (long long)N2 * inner, 1, inner, (long long)N2 * inner, 1, inner, inner, N2, T(1), tb->tw1,
-                        nullptr, st, SegStride(), SegStride(), o2, tb->twN, N - 1, pro, nullptr);
-  }
-  if (epi) { epi->idm = N1; epi->ido = 1; }     // output index k = k1 + N1*k2
-  FFB_REQUIRE(!pro, FFB_EINVAL, "internal: prologue on the second four-step sub-pass");
-  // length-N2 transforms over n2 (stride inner) for each k1 (outer stride N2*inner); output index k1 + N1*k2
-  o2.mod = N1;
-  return pow2_pass<T>(N2, C2C_COLS, dir, src, dst, inner, 1, (long long)N2 * inner, (long long)N1 * inner, 1, inner, inner, N1, scale, tb->tw2, nullptr,
-                      st, SegStride(), SegStride(), o2, nullptr, 0, nullptr, epi);
+  return fs_pass<T>(tb, part, inner, outer, src, dst, dir, scale, st, pro, epi);
 }
 
 // public ffb_fuse -> kernel hook for the strided pass along dimension d of a (e0, e1, e2) spectral array

@@ -28,7 +28,20 @@ inline int pow2_radices(int N, int* r) {
   }
   return 0;
 }
+// Float64 row passes with 8 points per thread (64 registers, 32 warps per SM instead of 16): radix sequence / availability
+inline int pow2_radices_r8(int N, int* r) {
+  switch (N) {
+    case 512: r[0] = 8; r[1] = 8; r[2] = 8; return 3;
+    case 1024: r[0] = 8; r[1] = 8; r[2] = 8; r[3] = 2; return 4;
+    case 2048: r[0] = 8; r[1] = 8; r[2] = 8; r[3] = 4; return 4;
+    case 4096: r[0] = 8; r[1] = 8; r[2] = 8; r[3] = 8; return 4;
+  }
+  return 0;
+}
 }  // namespace ffb
+
+// rows (C2C_ROWS / R2C_ROWS / C2R_ROWS) in Float64 with 8 points per thread; 1 = not instantiated
+int pow2_launch_double_r8(int N, int mode, int dir, const void* params, int gx, int gy, int threads, size_t smem, void* stream);
 
 #define FFB_POW2_DECL(tn, g) \
   int pow2_launch_##tn##_g##g(int N, int mode, int dir, const void* params, int gx, int gy, int threads, size_t smem, void* stream);

@@ -18,9 +18,15 @@ using real_t = FFB_REAL;
 // Float32: 32 data registers -> 1024 threads x 64 registers, so a CTA can own twice as many points.
 constexpr int kMaxT = sizeof(real_t) == 8 ? 512 : 1024;
 
+#if FFB_GROUP == 4
+constexpr int kMinBlocks = 2;   // R = 8 row plans: 512 threads x 64 registers, two CTAs (32 warps) per SM
+#else
+constexpr int kMinBlocks = 1;
+#endif
+
 template <int MODE, int DIR, int R, int... Rs>
 static int launch_one(const Pow2Params<real_t>& p, dim3 grid, int threads, size_t smem, cudaStream_t st) {
-  auto kern = fft_pow2_kernel<real_t, DIR, MODE, kMaxT, 1, R, Rs...>;
+  auto kern = fft_pow2_kernel<real_t, DIR, MODE, kMaxT, kMinBlocks, R, Rs...>;
   static size_t configured = 0;  // per instantiation
   if (smem > 48 * 1024 && smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -50,9 +56,22 @@ static int launch_n(int mode, int dir, const Pow2Params<real_t>& p, dim3 grid, i
   return set_error(FFB_EINVAL, "bad fft mode %d", mode);
 }
 
+// contiguous-line modes only (the R = 8 row plans of group 4)
+template <int R, int... Rs>
+static int launch_rows(int mode, int dir, const Pow2Params<real_t>& p, dim3 grid, int threads, size_t smem, cudaStream_t st) {
+  switch (mode) {
+    case C2C_ROWS: return dir < 0 ? launch_one<C2C_ROWS, -1, R, Rs...>(p, grid, threads, smem, st) : launch_one<C2C_ROWS, 1, R, Rs...>(p, grid, threads, smem, st);
+    case R2C_ROWS: return launch_one<R2C_ROWS, -1, R, Rs...>(p, grid, threads, smem, st);
+    case C2R_ROWS: return launch_one<C2R_ROWS, 1, R, Rs...>(p, grid, threads, smem, st);
+  }
+  return 1;
+}
+
 #define FFB_CAT2(a, b) a##b
 #define FFB_CAT(a, b) FFB_CAT2(a, b)
-#if FFB_GROUP == 0
+#if FFB_GROUP == 4
+#define FFB_FN(tn) FFB_CAT(FFB_CAT(pow2_launch_, tn), _r8)
+#elif FFB_GROUP == 0
 #define FFB_FN(tn) FFB_CAT(FFB_CAT(pow2_launch_, tn), _g0)
 #elif FFB_GROUP == 1
 #define FFB_FN(tn) FFB_CAT(FFB_CAT(pow2_launch_, tn), _g1)
@@ -65,7 +84,12 @@ static int launch_n(int mode, int dir, const Pow2Params<real_t>& p, dim3 grid, i
 // returns 1 if N is not handled by this group
 static int dispatch(int N, int mode, int dir, const Pow2Params<real_t>& p, dim3 grid, int threads, size_t smem, cudaStream_t st) {
   switch (N) {
-#if FFB_GROUP == 0
+#if FFB_GROUP == 4
+    case 512: return launch_rows<8, 8, 8, 8>(mode, dir, p, grid, threads, smem, st);
+    case 1024: return launch_rows<8, 8, 8, 8, 2>(mode, dir, p, grid, threads, smem, st);
+    case 2048: return launch_rows<8, 8, 8, 8, 4>(mode, dir, p, grid, threads, smem, st);
+    case 4096: return launch_rows<8, 8, 8, 8, 8>(mode, dir, p, grid, threads, smem, st);
+#elif FFB_GROUP == 0
     case 2: return launch_n<2, 2>(mode, dir, p, grid, threads, smem, st);
     case 4: return launch_n<4, 4>(mode, dir, p, grid, threads, smem, st);
     case 8: return launch_n<8, 8>(mode, dir, p, grid, threads, smem, st);

@@ -254,7 +254,7 @@ def test_fused_l2_four_step_matches_two_kernel_form_and_oracle(ff, shape, T, tol
     ref = fo.RfftPlan(shape, T) * x.astype(np.float64)
     outs = {}
     for mode in ("1", "0"):
-        monkeypatch.setenv("FFB_L2FOUR", mode)
+        monkeypatch.setenv("FFB_L2FOUR", mode)   # 1: one persistent kernel, intermediate in L2 (opt-in); 0: two kernels (default)
         plan = ff.Plan(shape, T, ff._lib.FFB_R2C)
         assert "four-step" in plan.describe()
         xh = plan * dev(ff, x)

@@ -12,7 +12,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import fourierflows_jl_b200 as ff  # noqa: E402
 from fourierflows_jl_b200 import _lib as L  # noqa: E402
 
-KEYS = ("FFB_L2FOUR", "FFB_L2_CHUNK", "FFB_L2_AHEAD", "FFB_FOURSTEP_MIN", "FFB_L2_PF", "FFB_L2_ACQ")
+KEYS = ("FFB_L2FOUR", "FFB_L2_CHUNK", "FFB_L2_AHEAD", "FFB_FOURSTEP_MIN", "FFB_L2_PF", "FFB_L2_ACQ", "FFB_ROWS_R8")
 
 
 def time_plan(shape, T, reps=8):
@@ -56,8 +56,8 @@ def main():
                 {"FFB_FOURSTEP_MIN": "1024"}, {"FFB_FOURSTEP_MIN": "1024", "FFB_L2FOUR": "0"}, {"FFB_FOURSTEP_MIN": "100000"}]
     if quick:
         cases = cases[:3]
-        variants = [{"FFB_L2FOUR": "0"}, {}, {"FFB_L2_PF": "0"}, {"FFB_L2_ACQ": "0"}, {"FFB_L2_CHUNK": "1"}, {"FFB_L2_CHUNK": "4"},
-                    {"FFB_L2_AHEAD": "10"}, {"FFB_L2_AHEAD": "15"}, {"FFB_L2_AHEAD": "15", "FFB_L2_CHUNK": "4"}]
+        cases = cases[:3] + [((1024, 1024, 256), f64), ((512, 512, 512), f64)]
+        variants = [{}, {"FFB_ROWS_R8": "0"}, {"FFB_L2FOUR": "1"}, {"FFB_L2FOUR": "1", "FFB_L2_ACQ": "0"}, {"FFB_FOURSTEP_MIN": "2048"}, {"FFB_FOURSTEP_MIN": "1024"}]
     for shape, T in cases:
         for v in variants:
             for k in KEYS:
