@@ -40,9 +40,9 @@ class CProblem:
         cfg.stepper = _STEPPER[stepper[len("Filtered"):] if filtered else stepper]
         cfg.filtered = 1 if filtered else 0
         fk = filter_kwargs or {}
-        if fk:
-            cfg.filter_order, cfg.filter_innerK = float(fk.get("order", 4)), float(fk.get("innerK", 2 / 3))
-            cfg.filter_outerK, cfg.filter_tol = float(fk.get("outerK", 1)), float(fk.get("tol", 1e-15))
+        # each keyword has its own "use the reference default" sentinel in ffb_problem_config (<= 0; innerK: < 0)
+        cfg.filter_order, cfg.filter_innerK = float(fk.get("order", 0.0)), float(fk.get("innerK", -1.0))
+        cfg.filter_outerK, cfg.filter_tol = float(fk.get("outerK", 0.0)), float(fk.get("tol", 0.0))
         cfg.dt = float(dt)
         cfg.calcN = _CALCN[calcN]
         self._cb = L.CALCN_FN(callback) if callback is not None else L.CALCN_FN()

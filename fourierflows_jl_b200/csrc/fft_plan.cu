@@ -203,6 +203,16 @@ static int build_tables(ffb_plan* pl) {
     else snprintf(buf, sizeof(buf), "dim%d:N=%d:%s ", d, N, tb->pow2 ? "pow2-register-stockham" : "generic-mixed-radix");
     pl->desc += buf;
   }
+  // a plan that mixes an arbitrary-size dimension (generic path: needs wN of EVERY dimension it touches) with a four-step-only
+  // power of two (no single-pass table) cannot execute: say so now, not at the first transform in the middle of a step
+  bool any_generic = false, any_four_only = false;
+  for (int d = 0; d < pl->ndim; ++d) {
+    auto* tb = reinterpret_cast<DimTables<T>*>(pl->tables[d]);
+    any_generic = any_generic || !tb->pow2;
+    any_four_only = any_four_only || (tb->four && !tb->tw);
+  }
+  if (any_generic && any_four_only)
+    return set_error(FFB_EUNSUPPORTED, "plan mixes an arbitrary-size dimension with a power-of-two dimension longer than %d (four-step only)", pow2_max_n(sizeof(T)));
   return FFB_OK;
 }
 

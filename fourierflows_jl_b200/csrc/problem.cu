@@ -355,8 +355,12 @@ int ffb_problem_create(ffb_problem** out, const ffb_problem_config* cfg) {
   if (cfg->filtered) {
     FFB_TRY(dalloc(p, &p->filter, p->rbytes, false));
     const double dx = roundT(p, cfg->L[0] / (double)p->n[0]), dy = roundT(p, cfg->L[1] / (double)p->n[1]), dz = roundT(p, cfg->L[2] / (double)p->n[2]);
-    const double order = cfg->filter_order > 0 ? cfg->filter_order : 4, innerK = cfg->filter_tol > 0 ? cfg->filter_innerK : 2.0 / 3.0;
-    const double outerK = cfg->filter_tol > 0 ? cfg->filter_outerK : 1.0, tol = cfg->filter_tol > 0 ? cfg->filter_tol : 1e-15;
+    // every filter parameter has its own "0 = reference default" sentinel (src/domains.jl:506: order=4, innerK=2/3, outerK=1, tol=1e-15);
+    // innerK = 0 is a legal value of the reference (test/test_grid.jl passes innerK=0): a NEGATIVE innerK selects the default
+    const double order = cfg->filter_order > 0 ? cfg->filter_order : 4;
+    const double outerK = cfg->filter_outerK > 0 ? cfg->filter_outerK : 1.0;
+    const double tol = cfg->filter_tol > 0 ? cfg->filter_tol : 1e-15;
+    const double innerK = (cfg->filter_innerK > 0 || (cfg->filter_innerK == 0 && (cfg->filter_outerK > 0 || cfg->filter_tol > 0))) ? cfg->filter_innerK : 2.0 / 3.0;
     FFB_TRY(ffb_make_filter(p->filter, p->kr, p->l, p->m, dx, p->nd >= 2 ? dy : 0, p->nd >= 3 ? dz : 0, order, innerK, outerK, tol, &D));
   }
   // state and stepper arrays (`zeros(dev, eqn.T, eqn.dims)`, src/problem.jl:108; @devzeros in each stepper constructor)

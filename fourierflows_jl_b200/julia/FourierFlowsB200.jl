@@ -243,7 +243,7 @@ coef(L::B200Array{Complex{S}}, T) where S = FFBCoef(L.ptr, 2, ffbtype(S), 0.0, 0
 fptr(ts) = hasproperty(ts, :filter) ? ts.filter.ptr : C_NULL
 
 # ---------------------------------------------------------------- B3: one stepforward! method per stepper TYPE (reference control flow kept)
-# (a `ts::Union{...}` signature would be ambiguous with the reference's `stepforward!(sol, clock, ts::XTimeStepper, ...)` methods:
+# (a union type in the `ts` argument would be ambiguous with the reference's `stepforward!(sol, clock, ts::XTimeStepper, ...)` methods:
 #  each concrete stepper type gets its own method, strictly more specific in `sol`)
 const B200Sol = B200Array
 

@@ -151,7 +151,7 @@ int ffb_plan_dist_set_peers(ffb_plan* plan, void* const* peers_buf0, void* const
 /* Exchange used by a slab-decomposed plan.  NCCL: chunked grouped send/recv (default, needs no peer mapping).
  * PEER_STORE: the fused pass described above; the receive layout is blocked ([kx block][z][y_local][B] forward,
  * [kx block][y][z_local][B] inverse, B complex = 64 bytes) so that a warp's stores are 256 contiguous bytes in the peer's
- * memory; needs 16 <= ny, nz <= 2048 and at most 16 ranks (FFB_EUNSUPPORTED otherwise).  COPY_ENGINE: the passes write
+ * memory; needs 16 <= ny, nz <= 2048 (Float32; 1024 in Float64) and at most 8 ranks -- one NVSwitch domain -- (FFB_EUNSUPPORTED otherwise).  COPY_ENGINE: the passes write
  * destination-major kx-chunks and cudaMemcpyAsync pushes them into the peers' receive buffers while the neighbouring
  * chunks are being transformed (no SM involved); a one-element all-reduce per chunk is the arrival barrier.
  * PEER_STORE and COPY_ENGINE need ffb_plan_dist_set_peers first. */
@@ -252,6 +252,9 @@ typedef struct {
   double aliased_fraction;
   int stepper;           /* ffb_stepper_kind */
   int filtered;          /* Filtered* variant; filter parameters below */
+  /* makefilter keywords (src/domains.jl:506).  Each field has its own sentinel: filter_order, filter_outerK, filter_tol <= 0 select the
+   * reference defaults (4, 1, 1e-15).  filter_innerK < 0 selects 2/3; filter_innerK == 0 means 0 when filter_outerK or filter_tol is
+   * given (> 0) and the default 2/3 in an all-zero (memset) configuration. */
   double filter_order, filter_innerK, filter_outerK, filter_tol;
   double dt;
   int calcN;             /* ffb_calcN_kind */

@@ -235,3 +235,20 @@ def test_fused_c_driven_vorticity_matches_oracle(ff, n, stepper):
     cb.stepforward(3)
     fo.stepforward(ob, 3)
     assert relerr(cb.sol.to_numpy(), ob.sol) <= 3e-12
+
+
+@pytest.mark.parametrize("fk", [dict(innerK=0.0, outerK=0.5), dict(order=2), dict(tol=1e-8), dict(innerK=0.4, outerK=0.9, order=6, tol=1e-12)],
+                         ids=["innerK0", "order", "tol", "all"])
+def test_c_driven_filter_keywords_each_have_their_own_default(ff, fk):
+    """`Problem(...; innerK, outerK, order, tol)` (makefilter keywords, src/domains.jl:506; test_instantiate_problem.jl:6-21): every
+    keyword of ffb_problem_config falls back to the reference default on its own, and innerK = 0 is honoured"""
+    n, nu, dt = 64, 1e-3, 2e-3
+    cp = ff.CProblem((n, n), 2 * np.pi, stepper="FilteredRK4", dt=dt, calcN="vorticity2d", nu=nu, filter_kwargs={k: fk.get(k, d) for k, d in
+                     (("order", 0.0), ("innerK", -1.0 if "innerK" not in fk else fk["innerK"]), ("outerK", 0.0), ("tol", 0.0))})
+    oprob = fo.TwoDNavierStokes.Problem(nx=n, nu=nu, dt=dt, stepper="FilteredRK4", **fk)
+    z0 = fo.random_phase_field((n, n), 2 * np.pi, 8.0, slope=-1, seed=1234)
+    cp.set_physical(z0)
+    oprob.grid.rfftplan.mul(oprob.sol, z0)
+    cp.stepforward(3)
+    fo.stepforward(oprob, 3)
+    assert relerr(cp.sol.to_numpy(), oprob.sol) <= 3e-12
