@@ -45,7 +45,7 @@ class ffb_desc(C.Structure):
 class ffb_fuse(C.Structure):
     _fields_ = [("cr", C.c_double), ("ci", C.c_double), ("kx", C.c_void_p), ("l", C.c_void_p), ("m", C.c_void_p), ("w", C.c_void_p),
                 ("acc", C.c_void_p), ("ar", C.c_double), ("ai", C.c_double), ("akx", C.c_void_p), ("al", C.c_void_p), ("am", C.c_void_p),
-                ("dealias", C.c_int), ("alias_lo", C.c_int32 * 3), ("alias_hi", C.c_int32 * 3), ("mul", C.c_void_p)]
+                ("dealias", C.c_int), ("alias_lo", C.c_int32 * 3), ("alias_hi", C.c_int32 * 3), ("mul", C.c_void_p), ("square_input", C.c_int)]
 
 
 CALCN_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p)
@@ -99,6 +99,7 @@ SIGNATURES = {
     "ffb_plan_dist_recv_buffers": [_vp, _P(_vp), _P(_vp), _P(_sz)],
     "ffb_plan_dist_set_peers": [_vp, _P(_vp), _P(_vp)],
     "ffb_plan_dist_set_exchange": [_vp, _i],
+    "ffb_plan_dist_get_exchange": [_vp, _P(_i)],
     "ffb_dist_ipc_export": [_vp, _vp, _P(_sz)],
     "ffb_dist_ipc_open": [_vp, _sz, _P(_vp)],
     "ffb_dist_ipc_close": [_vp],

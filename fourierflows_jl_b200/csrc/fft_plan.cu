@@ -130,7 +130,8 @@ static int build_fs_tw(int N, cx<T>** dev) {
 
 // Float64 row passes (dim 0) of 512 .. 4096 points have a second plan with 8 points per thread (64 registers, two 512-thread
 // CTAs = 32 warps per SM instead of 16: the row kernels are latency-bound).  pow2_pass finds it through the table of the
-// 16-point plan it is handed.  FFB_ROWS_R8=0 disables.
+// 16-point plan it is handed.  MEASURED SLOWER (8192^2 r2c 0.655 vs 0.593 ms: four passes / three two-phase exchanges with 16 warps per
+// barrier cost more than the extra warps hide): opt-in with FFB_ROWS_R8=1.
 static std::mutex g_tw8_mu;
 static std::map<const void*, const void*> g_tw8;
 static const void* rows_tw8_for(const void* tw) {
@@ -309,8 +310,10 @@ static int pow2_pass(int N, int mode, int dir, const void* in, void* out, long l
                      long long out_es, long long out_ls, long long out_os, long long nlines, long long nouter, T scale,
                      const cx<T>* tw, const cx<T>* twr, cudaStream_t st, SegStride in_seg = SegStride(), SegStride out_seg = SegStride(),
                      Outer2 o2 = Outer2(), const cx<T>* twN = nullptr, int twN_mask = 0,
-                     const typename Pow2Params<T>::Fuse* pro = nullptr, const typename Pow2Params<T>::Fuse* epi = nullptr, const T* rmul = nullptr) {
+                     const typename Pow2Params<T>::Fuse* pro = nullptr, const typename Pow2Params<T>::Fuse* epi = nullptr, const T* rmul = nullptr,
+                     int rsq = 0) {
   Pow2Params<T> p;
+  p.rsq = rsq;
   // plain strided passes: lean kernel variant with host-computed element offsets (needs segment lengths that are multiples of N/R)
   long long lean_out_off[16] = {0};
   static int lean_env = -1;
@@ -360,7 +363,7 @@ static int pow2_pass(int N, int mode, int dir, const void* in, void* out, long l
   p.twr = twr;
   int R = pow2_points_per_thread(N);
   bool r8 = false;
-  if (sizeof(T) == 8 && (mode == C2C_ROWS || mode == R2C_ROWS || mode == C2R_ROWS) && p.W == 1 && env_int("FFB_ROWS_R8", 1)) {
+  if (sizeof(T) == 8 && (mode == C2C_ROWS || mode == R2C_ROWS || mode == C2R_ROWS) && p.W == 1 && env_int("FFB_ROWS_R8", 0)) {
     if (const void* t8 = rows_tw8_for(tw)) { p.tw = reinterpret_cast<const cx<T>*>(t8); R = 8; r8 = true; }
   }
   const int threads = (N / R) * p.W;
@@ -420,12 +423,14 @@ static int pow2_pass(int N, int mode, int dir, const void* in, void* out, long l
 template <typename T>
 static int lean_tile_pass(int N, int dir, int W, const cx<T>* in, long long in_ts, long long in_os, long long in_es, const long long* in_off,
                           cx<T>* const* out_m, long long out_ts, long long out_os, long long out_es, long long nlines, long long nouter, T scale,
-                          const cx<T>* tw, cudaStream_t st) {
+                          const cx<T>* tw, cudaStream_t st, const typename Pow2Params<T>::Fuse* epi = nullptr) {
   Pow2Params<T> p;
+  p.rsq = 0;
   const int R = pow2_points_per_thread(N), Tn = N / R;
   FFB_REQUIRE(R == 16 && Tn * W <= pow2_max_threads(sizeof(T)) && nouter <= 65535, FFB_EUNSUPPORTED,
               "blocked strided pass: line length %d with %d-wide tiles is outside the kernel range", N, W);
   p.pro.on = 0; p.epi.on = 0; p.rmul = nullptr; p.reverse = 0; p.keep_out = 0;
+  if (epi) p.epi = *epi;
   p.in = in; p.out = nullptr;
   p.in_es = in_es; p.in_ls = 1; p.in_os = in_os; p.out_es = out_es; p.out_ls = 1; p.out_os = out_os;
   p.in_os2 = p.out_os2 = 0; p.outer_mod = 1 << 30;
@@ -724,7 +729,9 @@ static int exec_pow2(ffb_plan* pl, const void* in, void* out, int dir, const ffb
     g_pass_keep = (snake_enabled() && i + 1 < n) ? 1 : 0;
     int rc;
     if (op.kind == 0) rc = pow2_pass<T>(tb0->N, C2C_ROWS, dir, s_, d_, 1, tb0->N, 0, 1, tb0->N, 0, rows, 1, sc, tb0->tw, nullptr, st);
-    else if (op.kind == 1) rc = pow2_pass<T>(tb0->N, R2C_ROWS, -1, s_, d_, 1, tb0->N, 0, 1, e[0], 0, rows, 1, T(1), tb0->tw, tb0->twr, st);
+    else if (op.kind == 1)
+      rc = pow2_pass<T>(tb0->N, R2C_ROWS, -1, s_, d_, 1, tb0->N, 0, 1, e[0], 0, rows, 1, T(1), tb0->tw, tb0->twr, st, SegStride(), SegStride(), Outer2(),
+                        nullptr, 0, nullptr, nullptr, nullptr, (fuse && fuse->square_input) ? 1 : 0);
     else if (op.kind == 2)
       rc = pow2_pass<T>(tb0->N, C2R_ROWS, +1, s_, d_, 1, e[0], 0, 1, tb0->N, 0, rows, 1, sc, tb0->tw, tb0->twr, st, SegStride(), SegStride(), Outer2(),
                         nullptr, 0, nullptr, nullptr, fuse ? reinterpret_cast<const T*>(fuse->mul) : nullptr);
@@ -846,7 +853,7 @@ static int exec(ffb_plan* pl, const void* in, void* out, int dir) {
 //           no pack kernel) -> all-to-all over NCCL, chunked along z so chunk c's exchange overlaps chunk c+1's y-pass
 //           -> z c2c on the local y-slab.   inverse: mirrored (z, exchange, y, x c2r with 1/(nx ny nz)).
 template <typename T>
-static int exec_dist(ffb_plan* pl, const void* in, void* out, int dir) {
+static int exec_dist(ffb_plan* pl, const void* in, void* out, int dir, const ffb_fuse* fuse = nullptr) {
   cudaStream_t st = current_stream();
   FFB_REQUIRE(st, FFB_ECUDA, "no CUDA stream (no device?)");
   ffb_dist* d = pl->dist;
@@ -867,6 +874,21 @@ static int exec_dist(ffb_plan* pl, const void* in, void* out, int dir) {
   long double tot = (long double)pl->n[0] * ny * nz;
   const T inv = (T)(1.0L / tot);
   SegStride seg; seg.seg = (int)nyl; seg.stride = blk;
+  // fused forward transform (ffb_fft_forward_ex on a slab-decomposed plan): the real input is squared in the x pass, the
+  // spectral factor and the dealias mask are applied by the last (z) pass.  All coordinates are local: `l` and the y alias
+  // range are this rank's slices (the caller passes them that way, like every other per-slab operand).
+  const int rsq = (fuse && fuse->square_input) ? 1 : 0;
+  typename Pow2Params<T>::Fuse ehook;
+  const typename Pow2Params<T>::Fuse* epi = nullptr;
+  if (fuse) {
+    FFB_REQUIRE(dir < 0, FFB_EUNSUPPORTED, "fused transforms on slab-decomposed plans: forward only");
+    FFB_REQUIRE(!fuse->acc && !fuse->w && !fuse->mul, FFB_EUNSUPPORTED, "fused slab-decomposed forward transform: square_input, scalar / wavenumber factors and dealias only");
+    FFB_REQUIRE(pl->p2p != 2, FFB_EUNSUPPORTED, "fused transforms are not implemented for the copy-engine exchange");
+    const long long e[3] = {nkr, nyl, nz};
+    ehook = make_hook<T>(fuse, 2, 3, e, true);   // z pass: i0 = kx, other = y (local), transform index = z
+    ehook.idm = 1; ehook.ido = 0;
+    epi = &ehook;
+  }
   if (pl->p2p == 2) {
     // ---- copy-engine exchange, pipelined over kx-chunks: the pass before the exchange writes chunk c (a range of kx) in
     //      destination-rank-major order, cudaMemcpyAsync pushes the blocks into the peers' receive buffers over NVLink (no SM,
@@ -938,7 +960,8 @@ static int exec_dist(ffb_plan* pl, const void* in, void* out, int dir) {
     long long off[16];
     cx<T>* dst[16];
     if (dir < 0) {
-      if ((rc = pow2_pass<T>(N0, R2C_ROWS, -1, in, w0, 1, N0, 0, 1, nkr, 0, ny * nzl, 1, T(1), tb0->tw, tb0->twr, st))) return rc;
+      if ((rc = pow2_pass<T>(N0, R2C_ROWS, -1, in, w0, 1, N0, 0, 1, nkr, 0, ny * nzl, 1, T(1), tb0->tw, tb0->twr, st, SegStride(), SegStride(), Outer2(),
+                             nullptr, 0, nullptr, nullptr, nullptr, rsq))) return rc;
       // y: w0 (nkr, ny, nzl) -> rank (y / nyl)'s buffer, layout [kt][z][yl][B] with z = rank*nzl + zl
       for (int m = 0; m < 16; ++m) {
         const long long y = (long long)m * Tny;
@@ -954,7 +977,7 @@ static int exec_dist(ffb_plan* pl, const void* in, void* out, int dir) {
         off[m] = z * nyl * B;
         dst[m] = reinterpret_cast<cx<T>*>(out) + z * nkr * nyl;
       }
-      return lean_tile_pass<T>((int)nz, -1, B, mine, nz * nyl * B, B, nyl * B, off, dst, B, nkr, nkr * nyl, nkr, nyl, T(1), tb2->tw, st);
+      return lean_tile_pass<T>((int)nz, -1, B, mine, nz * nyl * B, B, nyl * B, off, dst, B, nkr, nkr * nyl, nkr, nyl, T(1), tb2->tw, st, epi);
     }
     // z: in (nkr, nyl, nz) -> rank (z / nzl)'s buffer, layout [kt][y][zl][B] with y = rank*nyl + yl
     for (int m = 0; m < 16; ++m) {
@@ -978,7 +1001,8 @@ static int exec_dist(ffb_plan* pl, const void* in, void* out, int dir) {
   if (dir < 0) {
     cx<T>* spec = reinterpret_cast<cx<T>*>(out);
     // x: real (nx, ny, nzl) -> w0 (nkr, ny, nzl)
-    if ((rc = pow2_pass<T>(N0, R2C_ROWS, -1, in, w0, 1, N0, 0, 1, nkr, 0, ny * nzl, 1, T(1), tb0->tw, tb0->twr, st))) return rc;
+    if ((rc = pow2_pass<T>(N0, R2C_ROWS, -1, in, w0, 1, N0, 0, 1, nkr, 0, ny * nzl, 1, T(1), tb0->tw, tb0->twr, st, SegStride(), SegStride(), Outer2(),
+                           nullptr, 0, nullptr, nullptr, nullptr, rsq))) return rc;
     for (int c = 0; c < nch; ++c) {
       // y on z-chunk c: w0 -> w1 laid out [peer][kx, y_local, z_local]
       if ((rc = pow2_pass<T>((int)ny, C2C_COLS, -1, w0 + c * zc * nkr * ny, w1 + c * sub, nkr, 1, nkr * ny, nkr, 1, nkr * nyl, nkr, zc, T(1), tb1->tw,
@@ -993,7 +1017,9 @@ static int exec_dist(ffb_plan* pl, const void* in, void* out, int dir) {
     FFB_CUDA(cudaEventRecord(e, d->comm_stream));
     FFB_CUDA(cudaStreamWaitEvent(st, e, 0));
     // z on the local y-slab, in place: (nkr*nyl) columns of length nz
-    return pow2_pass<T>((int)nz, C2C_COLS, -1, spec, spec, nkr * nyl, 1, 0, nkr * nyl, 1, 0, nkr * nyl, 1, T(1), tb2->tw, nullptr, st);
+    if (epi) { ehook.other_from_col = 1; ehook.n0 = (int)nkr; }   // plain layout: column = kx + nkr * y_local
+    return pow2_pass<T>((int)nz, C2C_COLS, -1, spec, spec, nkr * nyl, 1, 0, nkr * nyl, 1, 0, nkr * nyl, 1, T(1), tb2->tw, nullptr, st, SegStride(), SegStride(),
+                        Outer2(), nullptr, 0, nullptr, epi);
   }
   // inverse
   const cx<T>* spec = reinterpret_cast<const cx<T>*>(in);
@@ -1147,6 +1173,12 @@ int ffb_plan_dist_set_exchange(ffb_plan* pl, int mode) {
   return FFB_OK;
 }
 
+int ffb_plan_dist_get_exchange(const ffb_plan* pl, int* mode) {
+  FFB_REQUIRE(pl && pl->dist && mode, FFB_EINVAL, "needs a slab-decomposed plan");
+  *mode = pl->p2p;
+  return FFB_OK;
+}
+
 int ffb_plan_destroy(ffb_plan* pl) {
   if (!pl) return FFB_OK;
   if (pl->dtype == FFB_F64) free_tables<double>(pl); else free_tables<float>(pl);
@@ -1185,7 +1217,7 @@ int ffb_fft_forward(ffb_plan* pl, const void* in, void* out) {
 static int exec_fused(ffb_plan* pl, const void* in, void* out, int dir, const ffb_fuse* fuse) {
   FFB_REQUIRE(pl && in && out && fuse, FFB_EINVAL, "NULL argument");
   FFB_REQUIRE(in != out, FFB_EINVAL, "fused transforms are out of place");
-  FFB_REQUIRE(!pl->dist, FFB_EUNSUPPORTED, "fused transforms on slab-decomposed plans are not implemented");
+  if (pl->dist) return pl->dtype == FFB_F64 ? exec_dist<double>(pl, in, out, dir, fuse) : exec_dist<float>(pl, in, out, dir, fuse);
   bool allp = true;
   for (int d = 0; d < pl->ndim; ++d) {
     if (pl->dtype == FFB_F64) { auto* tb = reinterpret_cast<DimTables<double>*>(pl->tables[d]); allp = allp && tb->pow2 && (tb->four || tb->tw); }

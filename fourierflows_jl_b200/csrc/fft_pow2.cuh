@@ -56,6 +56,7 @@ struct Pow2Params {
   };
   Fuse pro, epi;
   const T* rmul;                     // C2R_ROWS: real result multiplied by this real field (same layout as out)
+  int rsq;                           // R2C_ROWS: the real input is squared on load (`@. c = c * c` folded into the transform)
   int pf_ahead;                      // ROWS modes: prefetch the line this many tiles ahead into L2 (0 = off)
   int reverse;                       // walk tiles / slices backwards (snake ordering between consecutive passes: the tail
                                      // of what the previous kernel wrote is still in the 126 MB L2)
@@ -378,6 +379,12 @@ FFB_D void fft_pow2_tile(const Pow2Params<T>& p, const unsigned bx, const unsign
       const int i = t + m * Tn;
       v[m] = active ? ldin<T, IN_CG>(in + (long long)(i & p.in_seg_mask) * p.in_es + (long long)(i >> p.in_seg_shift) * p.in_seg_stride) : mk<T>(0, 0);
     }
+    if constexpr (MODE == R2C_ROWS) {
+      if (p.rsq) {   // a packed pair of reals: square each
+#pragma unroll
+        for (int m = 0; m < R; ++m) v[m] = mk<T>(v[m].x * v[m].x, v[m].y * v[m].y);
+      }
+    }
     after_load();
     if (p.pro.on && active) {
       const int i0 = (int)(line % p.pro.n0);
@@ -462,7 +469,24 @@ FFB_D void fft_pow2_tile(const Pow2Params<T>& p, const unsigned bx, const unsign
     if (active) {
       const long long oo = (long long)by * p.out_os + (long long)bx * p.out_ts + w + (long long)t * p.out_es;
       const T sc = p.scale;
-      if (sc != T(1)) {
+      if (p.epi.on) {
+        // epilogue of the blocked strided passes (slab decomposition): out = dealias( (cr + i ci) * k0[line] * ko[by] * kt[it] * y ),
+        // coordinates: line = tile column (kx), by = outer slice, it = transform index
+        const typename Pow2Params<T>::Fuse& h = p.epi;
+        const int i0 = (int)line, io = (int)by;
+        const bool dead0 = h.dealias && ((h.lo0 > 0 && i0 >= h.lo0 - 1 && i0 < h.hi0) || (h.loo > 0 && io >= h.loo - 1 && io < h.hio));
+        T fr0 = h.cr, fi0 = h.ci;
+        if (h.k0) { const T q = __ldg(h.k0 + i0); fr0 *= q; fi0 *= q; }
+        if (h.ko) { const T q = __ldg(h.ko + io); fr0 *= q; fi0 *= q; }
+#pragma unroll
+        for (int m = 0; m < R; ++m) {
+          const int it = t + m * Tn;
+          const bool dead = dead0 || (h.dealias && h.lot > 0 && it >= h.lot - 1 && it < h.hit);
+          T fr = fr0, fi = fi0;
+          if (h.kt) { const T q = __ldg(h.kt + it); fr *= q; fi *= q; }
+          stk(p.out_m[m] + oo, dead ? mk<T>(0, 0) : mk<T>(fr, fi) * (sc * v[m]), p.keep_out);
+        }
+      } else if (sc != T(1)) {
 #pragma unroll
         for (int m = 0; m < R; ++m) stk(p.out_m[m] + oo, sc * v[m], p.keep_out);
       } else {

@@ -170,18 +170,22 @@ static int calcN_impl(ffb_problem* p, void* N, const void* sol, double t) {
     case FFB_CALCN_BURGERS3D: {
       // N = -1/2 im kr rfft(irfft(sol)^2) ; dealias!(N, grid)   (builder-defined 3-D test equation)
       if ((rc = ffb_fft_inverse(p->plan, sol, p->ph1))) return rc;
+      int exch = 0;
+      if (p->cfg.dist) ffb_plan_dist_get_exchange(p->plan, &exch);
+      if (p->cfg.fused && exch != FFB_EXCHANGE_COPY_ENGINE) {
+        // the square is folded into the x pass (r2c load), `-1/2 im kr` and the dealias mask into the last pass's store:
+        // no elementwise kernel at all, also on slab-decomposed plans
+        ffb_fuse f;
+        memset(&f, 0, sizeof(f));
+        f.cr = 0.0; f.ci = -0.5; f.kx = p->kr; f.dealias = 1; f.square_input = 1;
+        for (int q = 0; q < 3; ++q) { f.alias_lo[q] = d->alias_lo[q]; f.alias_hi[q] = d->alias_hi[q]; }
+        return ffb_fft_forward_ex(p->plan, p->ph1, N, &f);
+      }
       const unsigned blocks = (unsigned)std::min<long long>((p->nphys / 4 + 255) / 256, (long long)num_sms() * 16);
       { ProfScope ps("calcN_square", 2.0 * p->pbytes);
       square_real_kernel<T><<<blocks, 256, 0, s>>>((T*)p->ph1, p->nphys);
       count_launch(); }
       FFB_CHECK_LAUNCH();
-      if (p->cfg.fused && !p->cfg.dist) {
-        ffb_fuse f;
-        memset(&f, 0, sizeof(f));
-        f.cr = 0.0; f.ci = -0.5; f.kx = p->kr; f.dealias = 1;
-        for (int q = 0; q < 3; ++q) { f.alias_lo[q] = d->alias_lo[q]; f.alias_hi[q] = d->alias_hi[q]; }
-        return ffb_fft_forward_ex(p->plan, p->ph1, N, &f);
-      }
       if ((rc = ffb_fft_forward(p->plan, p->ph1, p->sh1))) return rc;
       return ffb_ew_spectral_mul(N, p->sh1, 0.0, -0.5, p->kr, 1, nullptr, 0, nullptr, 0, nullptr, 0, 1, d);
     }

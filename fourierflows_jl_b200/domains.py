@@ -70,7 +70,7 @@ class Plan:
 
     # fused forms (ffb_fft_forward_ex / ffb_fft_inverse_ex): spectral multiplies, products and dealias folded into the passes
     @staticmethod
-    def _fuse(coef=1.0, kx=None, l=None, m=None, w=None, acc=None, acoef=0.0, akx=None, al=None, am=None, alias=None, mul=None):
+    def _fuse(coef=1.0, kx=None, l=None, m=None, w=None, acc=None, acoef=0.0, akx=None, al=None, am=None, alias=None, mul=None, square=False):
         f = L.ffb_fuse()
         c, a = complex(coef), complex(acoef)
         f.cr, f.ci, f.ar, f.ai = c.real, c.imag, a.real, a.imag
@@ -80,6 +80,7 @@ class Plan:
         al3 = list(alias) + [None] * (3 - len(alias)) if alias is not None else [None] * 3
         f.alias_lo = (C.c_int32 * 3)(*[(r[0] if r else 0) for r in al3])
         f.alias_hi = (C.c_int32 * 3)(*[(r[1] if r else 0) for r in al3])
+        f.square_input = 1 if square else 0
         return f
 
     def ldiv_ex(self, out: DevArray, ah: DevArray, coef=1.0, kx=None, l=None, m=None, w=None, mul=None):
@@ -89,10 +90,10 @@ class Plan:
         return out
 
     def mul_ex(self, out: DevArray, a: DevArray, coef=1.0, kx=None, l=None, m=None, w=None, acc=None, acoef=0.0, akx=None, al=None, am=None,
-               alias=None):
+               alias=None, square=False):
         """`out = dealias!((coef * kx * l * m * w) .* rfft(a) + (acoef * akx * al * am) .* acc)`; `alias` = per-dimension
-        1-based ranges (kralias, lalias[, malias]) or None."""
-        f = self._fuse(coef=coef, kx=kx, l=l, m=m, w=w, acc=acc, acoef=acoef, akx=akx, al=al, am=am, alias=alias)
+        1-based ranges (kralias, lalias[, malias]) or None; `square`: transform `a.^2`."""
+        f = self._fuse(coef=coef, kx=kx, l=l, m=m, w=w, acc=acc, acoef=acoef, akx=akx, al=al, am=am, alias=alias, square=square)
         L.call("ffb_fft_forward_ex", self._h, a.ptr, out.ptr, C.byref(f))
         return out
 

@@ -521,6 +521,7 @@ struct FFBFuse
   akx :: Ptr{Cvoid}; al :: Ptr{Cvoid}; am :: Ptr{Cvoid}
   dealias :: Cint; alias_lo :: NTuple{3,Int32}; alias_hi :: NTuple{3,Int32}
   mul :: Ptr{Cvoid}
+  square_input :: Cint
 end
 "`ldiv!(out, plan, ah, fuse)`: out = irfft(factor .* ah) [.* mul];  `mul!(outh, plan, a, fuse)`: outh = factor .* rfft(a) [+ g .* acc] [dealiased]"
 ldiv!(out::B200Array, p::B200Plan, ah::B200Array, f::FFBFuse) =

@@ -111,6 +111,9 @@ int ffb_fft_inverse(ffb_plan* plan, const void* in, void* out);
  * physical-space products are folded into the FFT passes).  All-power-of-two plans with ndim >= 2 only.
  *   inverse_ex:  out = irfft( F .* in ) .* mul       F[k,l,m] = (cr + i ci) * kx[k] * l[l] * m[m] * w[k,l,m]
  *   forward_ex:  out = dealias!( F .* rfft(in) + G .* acc )   G = (ar + i ai) * akx[k] * al[l] * am[m]
+ * forward_ex with square_input != 0 transforms in.^2.  On slab-decomposed plans forward_ex supports square_input, the scalar /
+ * wavenumber factors and dealias (l = this rank's slice of the y wavenumbers, alias range 1 = the local range; no acc / w; NCCL and
+ * peer-store exchanges).
  * Any vector / array pointer may be NULL (factor 1).  `w`, `acc` have the layout of the spectral array, `mul` of the
  * physical array.  dealias != 0 zeroes the alias box given by alias_lo/hi (as in ffb_desc). */
 typedef struct {
@@ -122,6 +125,7 @@ typedef struct {
   int dealias;
   int32_t alias_lo[3], alias_hi[3];
   const void* mul;
+  int square_input;   /* forward_ex: the real input is squared on load (`@. c = c * c` before `mul!`) */
 } ffb_fuse;
 int ffb_fft_forward_ex(ffb_plan* plan, const void* in, void* out, const ffb_fuse* fuse);
 int ffb_fft_inverse_ex(ffb_plan* plan, const void* in, void* out, const ffb_fuse* fuse);
@@ -157,6 +161,7 @@ int ffb_plan_dist_set_peers(ffb_plan* plan, void* const* peers_buf0, void* const
  * PEER_STORE and COPY_ENGINE need ffb_plan_dist_set_peers first. */
 enum { FFB_EXCHANGE_NCCL = 0, FFB_EXCHANGE_PEER_STORE = 1, FFB_EXCHANGE_COPY_ENGINE = 2 };
 int ffb_plan_dist_set_exchange(ffb_plan* plan, int mode);
+int ffb_plan_dist_get_exchange(const ffb_plan* plan, int* mode);
 /* export: handle of the allocation that holds dev_ptr + offset of dev_ptr inside it; open: maps the allocation once per
  * process (reference counted) and returns base + offset; close: drops one reference */
 int ffb_dist_ipc_export(void* dev_ptr, void* host_handle64, size_t* offset);

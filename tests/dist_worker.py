@@ -47,14 +47,19 @@ def main():
             if rank == 0:
                 print(f"dist fft {shape} {np.dtype(T).name} chunks={nch}: fwd {e1:.2e} rt {e2:.2e} [{plan.describe()}]", flush=True)
     # slab-decomposed Burgers problem (configs C4 / C5 shape), C-driven, vs the single-process oracle
-    for stepper, T, tol in (("FilteredRK4", np.float64, 1e-12), ("ETDRK4", np.float32, 1e-5), ("LSRK54", np.float32, 1e-5)):
+    # fused = 1: square folded into the x pass, -1/2 im kr and the dealias mask into the last z pass (NCCL and peer-store exchanges;
+    # the copy-engine exchange runs the unfused kernels)
+    for stepper, T, tol, exch, fused in (("FilteredRK4", np.float64, 1e-12, "copy-engine", 0), ("ETDRK4", np.float32, 1e-5, "peer-store", 0),
+                                         ("LSRK54", np.float32, 1e-5, None, 0), ("ETDRK4", np.float32, 1e-5, "peer-store", 1),
+                                         ("FilteredRK4", np.float64, 1e-12, "peer-store", 1), ("LSRK54", np.float64, 1e-12, None, 1),
+                                         ("RK4", np.float64, 1e-12, "copy-engine", 1)):
         n = (64, 64, 64)
         ob = fo.Burgers3D.Problem(nx=64, kappa=1e-3, dt=1e-3, stepper=stepper, T=T)
         c0 = fo.random_phase_field(n, 2 * np.pi, 4.0, slope=0, seed=1234, T=T)
         ob.grid.rfftplan.mul(ob.sol, c0)
-        cp = ff.CProblem(n, 2 * np.pi, stepper=stepper, dt=1e-3, calcN="burgers3d", nu=1e-3, T=T, dist=comm)
-        if stepper != "LSRK54":
-            cp.enable_p2p("peer-store" if stepper == "ETDRK4" else "copy-engine")
+        cp = ff.CProblem(n, 2 * np.pi, stepper=stepper, dt=1e-3, calcN="burgers3d", nu=1e-3, T=T, dist=comm, fused=fused)
+        if exch is not None:
+            cp.enable_p2p(exch)
         cp.set_physical(ff.physical_slab(c0, P, rank))
         for s in range(3):
             cp.stepforward(1)
@@ -67,7 +72,7 @@ def main():
             e = float(torch.sqrt(acc[0] / acc[1]).item())
             worst = max(worst, e / ((s + 1) * tol))
         if rank == 0:
-            print(f"dist burgers {stepper} {np.dtype(T).name}: rel-L2 after 3 steps {e:.2e}", flush=True)
+            print(f"dist burgers {stepper} {np.dtype(T).name} exchange={exch or 'nccl'} fused={fused}: rel-L2 after 3 steps {e:.2e}", flush=True)
     t = torch.tensor([worst], device="cuda", dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ok = float(t.item()) <= 1.0

@@ -60,8 +60,10 @@ def test_unsupported_decompositions_fail_loudly(ff):
     comm.close()
 
 
-@pytest.mark.parametrize("P", [2, 4, 8])
+@pytest.mark.parametrize("P", [1, 2, 4, 8])
 def test_multi_gpu_worker(P):
+    """torchrun worker: every exchange (NCCL, copy-engine, peer-store, autotuned) and the fused slab-decomposed Burgers problem against the
+    oracle.  P = 1 runs on the single-GPU box too (the rank is its own peer: same kernels, same blocked layouts, IPC-free)."""
     if ngpus() < P:
         pytest.skip(f"needs {P} GPUs")
     env = dict(os.environ)
