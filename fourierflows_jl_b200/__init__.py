@@ -19,6 +19,7 @@ from .utils import axpby, mul_real, parsevalsum, parsevalsum2, spectral_mul
 from . import diffusion as Diffusion
 from .equations import Burgers3D, TwoDNavierStokes
 from .cproblem import CProblem
-from .dist import Dist, DistPlan, exchange_bytes_per_rank, local_alias_range, physical_slab, slab_range, spectral_slab
+from .dist import (Dist, DistPlan, exchange_bytes_per_rank, gather_spectral_2d, local_alias_range, local_kx_alias_2d, physical_slab,
+                   physical_slab_2d, slab_range, spectral_slab, spectral_slab_2d)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

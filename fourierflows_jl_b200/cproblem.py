@@ -24,7 +24,10 @@ class CProblem:
         self.nkr = n[0] // 2 + 1
         self.dist = dist
         P = dist.nranks if dist is not None else 1
-        if dist is not None:
+        if dist is not None and len(n) == 2:
+            self.spectral_shape = (n[0] // 2 // P + 1, n[1])      # kx block + the Nyquist / padding column (dist.spectral_slab_2d)
+            self.physical_shape = (n[0], n[1] // P)               # y-slab
+        elif dist is not None:
             self.spectral_shape = (self.nkr, n[1] // P, n[2])     # y-slab
             self.physical_shape = (n[0], n[1], n[2] // P)         # z-slab
         else:

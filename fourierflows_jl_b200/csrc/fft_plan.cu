@@ -83,7 +83,9 @@ struct ffb_plan {
   size_t ws_bytes;    // size of each scratch array
   std::string desc;
   ffb_dist* dist;     // non-NULL: slab-decomposed 3-D r2c plan (physical z-slabs <-> spectral y-slabs)
-  long long nyl, nzl; // local extents: spectral (nkr, nyl, nz), physical (nx, ny, nzl)
+  long long nyl, nzl; // local extents: spectral (nkr, nyl, nz), physical (nx, ny, nzl); 2-D: physical (nx, nyl)
+  long long kb;       // 2-D slab decomposition: wavenumbers per rank block (local spectral slab: (kb + 1, ny))
+  int ws0_zeroed;
   int nchunks;        // exchange chunks along the local z range (overlap of all-to-all and local passes)
   // fused pass + collective: double-buffered receive buffers and their peer mappings (CUDA IPC)
   void* recv[2];
@@ -302,6 +304,9 @@ static int snake_enabled() {
 }
 
 struct SegStride { int seg = 0; long long stride = 0; };  // seg = 0: unsegmented
+// half spectrum of the next row pass cut into per-rank blocks (2-D slab decomposition; set around the call by exec_dist2d)
+struct RowSeg { int seg = 0; long long stride = 0, nyq = 0; };
+static thread_local RowSeg g_row_seg;
 // two-level outer index (four-step sub-passes): blockIdx.y = o_lo + mod*o_hi -> o_lo*os + o_hi*os2
 struct Outer2 { int mod = 0; long long nhi = 1, in_os2 = 0, out_os2 = 0; };
 
@@ -314,6 +319,8 @@ static int pow2_pass(int N, int mode, int dir, const void* in, void* out, long l
                      int rsq = 0) {
   Pow2Params<T> p;
   p.rsq = rsq;
+  p.row_seg = g_row_seg.seg; p.row_seg_mask = g_row_seg.seg ? g_row_seg.seg - 1 : 0; p.row_seg_shift = g_row_seg.seg ? ilog2((uint64_t)g_row_seg.seg) : 0;
+  p.row_seg_stride = g_row_seg.stride; p.row_nyq = g_row_seg.nyq;
   // plain strided passes: lean kernel variant with host-computed element offsets (needs segment lengths that are multiples of N/R)
   long long lean_out_off[16] = {0};
   static int lean_env = -1;
@@ -425,7 +432,7 @@ static int lean_tile_pass(int N, int dir, int W, const cx<T>* in, long long in_t
                           cx<T>* const* out_m, long long out_ts, long long out_os, long long out_es, long long nlines, long long nouter, T scale,
                           const cx<T>* tw, cudaStream_t st, const typename Pow2Params<T>::Fuse* epi = nullptr) {
   Pow2Params<T> p;
-  p.rsq = 0;
+  p.rsq = 0; p.row_seg = 0; p.row_seg_mask = 0; p.row_seg_shift = 0; p.row_seg_stride = 0; p.row_nyq = 0;
   const int R = pow2_points_per_thread(N), Tn = N / R;
   FFB_REQUIRE(R == 16 && Tn * W <= pow2_max_threads(sizeof(T)) && nouter <= 65535, FFB_EUNSUPPORTED,
               "blocked strided pass: line length %d with %d-wide tiles is outside the kernel range", N, W);
@@ -1044,6 +1051,79 @@ static int exec_dist(ffb_plan* pl, const void* in, void* out, int dir, const ffb
   return FFB_OK;
 }
 
+// ---------------------------------------------------------------- slab-decomposed 2-D r2c / c2r ("2-D grids beyond one GPU")
+// physical (nx, ny) is split along y: rank r holds (nx, ny/P); the half spectrum is split along kx into blocks of kb = nx/(2P)
+// wavenumbers, the Nyquist wavenumber riding with the last block: every rank holds a (kb + 1, ny) array whose last column is the
+// Nyquist column on rank P-1 and zero padding elsewhere (equal blocks: the exchange is a plain all-to-all, no pack / unpack).
+//   forward: x r2c on the local rows, each line's half spectrum stored block by block in destination-rank-major order
+//            -> all-to-all straight into `out` -> y c2c in place on the (kb + 1, ny) slab (four-step for long lines, fusion hooks)
+//   inverse: y c2c into scratch -> all-to-all -> x c2r reading the per-rank blocks
+template <typename T>
+static int exec_dist2d(ffb_plan* pl, const void* in, void* out, int dir, const ffb_fuse* fuse = nullptr) {
+  cudaStream_t st = current_stream();
+  FFB_REQUIRE(st, FFB_ECUDA, "no CUDA stream (no device?)");
+  ffb_dist* d = pl->dist;
+  const int P = d->nranks;
+  auto* tb0 = reinterpret_cast<DimTables<T>*>(pl->tables[0]);
+  auto* tb1 = reinterpret_cast<DimTables<T>*>(pl->tables[1]);
+  const long long ny = pl->n[1], nyl = pl->nyl, kb = pl->kb, nkl = kb + 1;
+  const int N0 = tb0->N;
+  const long long blk = nkl * nyl;               // complex elements exchanged with each peer
+  int rc = ensure_ws(pl, 3);
+  if (rc) return rc;
+  cx<T>* w0 = reinterpret_cast<cx<T>*>(pl->ws[0]);   // forward send buffer: its padding columns are zero and never written
+  cx<T>* w1 = reinterpret_cast<cx<T>*>(pl->ws[1]);
+  cx<T>* w2 = reinterpret_cast<cx<T>*>(pl->ws[2]);
+  if (!pl->ws0_zeroed) { FFB_CUDA(cudaMemsetAsync(w0, 0, pl->ws_bytes, st)); pl->ws0_zeroed = 1; }
+  const T inv = (T)(1.0L / ((long double)pl->n[0] * (long double)ny));
+  const long long e[3] = {nkl, ny, 1};
+  RowSeg rs; rs.seg = (int)kb; rs.stride = blk; rs.nyq = (long long)(P - 1) * blk + kb;
+  // y pass over the (nkl, ny) slab: single pass, or the four-step pair through w1 (sub-pass A may run in place, B may not)
+  auto y_pass = [&](const cx<T>* src, cx<T>* dst, cx<T>* tmp, int sign, T scale, typename Pow2Params<T>::Fuse* pro, typename Pow2Params<T>::Fuse* epi) -> int {
+    if (!tb1->four) return cols_pass<T>(pl, tb1, 0, nkl, 1, src, dst, sign, scale, st, pro, epi);
+    if (l2four_enabled(tb1->N1, tb1->N2)) return cols_pass<T>(pl, tb1, 4, nkl, 1, src, dst, sign, scale, st, pro, epi);
+    int r = cols_pass<T>(pl, tb1, 1, nkl, 1, src, tmp, sign, T(1), st, pro, nullptr);
+    if (r) return r;
+    return cols_pass<T>(pl, tb1, 2, nkl, 1, tmp, dst, sign, scale, st, nullptr, epi);
+  };
+  typename Pow2Params<T>::Fuse hook;
+  if (dir < 0) {
+    g_row_seg = rs;
+    rc = pow2_pass<T>(N0, R2C_ROWS, -1, in, w0, 1, N0, 0, 1, nkl, 0, nyl, 1, T(1), tb0->tw, tb0->twr, st, SegStride(), SegStride(), Outer2(), nullptr, 0,
+                      nullptr, nullptr, nullptr, (fuse && fuse->square_input) ? 1 : 0);
+    g_row_seg = RowSeg();
+    if (rc) return rc;
+    cx<T>* spec = reinterpret_cast<cx<T>*>(out);
+    const bool four2 = tb1->four && !l2four_enabled(tb1->N1, tb1->N2);
+    cx<T>* land = four2 ? w1 : spec;   // the two-kernel four-step needs its input outside `out`
+    { ProfScope ps("nccl_alltoall", 0);
+    if ((rc = dist_alltoall_bytes(d, w0, land, (size_t)blk * sizeof(cx<T>), (size_t)blk * sizeof(cx<T>), st))) return rc; }
+    typename Pow2Params<T>::Fuse* epi = nullptr;
+    if (fuse) { hook = make_hook<T>(fuse, 1, 2, e, true); epi = &hook; }
+    if (four2) {
+      if ((rc = cols_pass<T>(pl, tb1, 1, nkl, 1, w1, w1, -1, T(1), st, nullptr, nullptr))) return rc;   // A in place
+      return cols_pass<T>(pl, tb1, 2, nkl, 1, w1, spec, -1, T(1), st, nullptr, epi);
+    }
+    return y_pass(spec, spec, w1, -1, T(1), nullptr, epi);
+  }
+  // inverse
+  const bool want_pro = fuse && (fuse->kx || fuse->l || fuse->w || fuse->cr != 1.0 || fuse->ci != 0.0);
+  typename Pow2Params<T>::Fuse* pro = nullptr;
+  if (want_pro) { hook = make_hook<T>(fuse, 1, 2, e, false); pro = &hook; }
+  const cx<T>* spec = reinterpret_cast<const cx<T>*>(in);
+  if (tb1->four && !l2four_enabled(tb1->N1, tb1->N2)) {
+    if ((rc = cols_pass<T>(pl, tb1, 1, nkl, 1, spec, w2, +1, T(1), st, pro, nullptr))) return rc;
+    if ((rc = cols_pass<T>(pl, tb1, 2, nkl, 1, w2, w1, +1, T(1), st, nullptr, nullptr))) return rc;
+  } else if ((rc = y_pass(spec, w1, w2, +1, T(1), pro, nullptr))) return rc;
+  { ProfScope ps("nccl_alltoall", 0);
+  if ((rc = dist_alltoall_bytes(d, w1, w2, (size_t)blk * sizeof(cx<T>), (size_t)blk * sizeof(cx<T>), st))) return rc; }
+  g_row_seg = rs;
+  rc = pow2_pass<T>(N0, C2R_ROWS, +1, w2, out, 1, nkl, 0, 1, N0, 0, nyl, 1, inv, tb0->tw, tb0->twr, st, SegStride(), SegStride(), Outer2(), nullptr, 0,
+                    nullptr, nullptr, fuse ? reinterpret_cast<const T*>(fuse->mul) : nullptr);
+  g_row_seg = RowSeg();
+  return rc;
+}
+
 }  // namespace ffb
 
 extern "C" {
@@ -1065,7 +1145,7 @@ int ffb_plan_create(ffb_plan** out, int ndim, const int64_t* n, int dtype, int k
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return set_error(FFB_ECUDA, "no CUDA device"); }
   auto* pl = new ffb_plan();
   pl->ndim = ndim; pl->dtype = dtype; pl->kind = kind; pl->nbatch = nbatch; pl->flags = flags;
-  pl->dist = nullptr; pl->nyl = pl->nzl = 0; pl->nchunks = 1;
+  pl->dist = nullptr; pl->nyl = pl->nzl = 0; pl->nchunks = 1; pl->kb = 0; pl->ws0_zeroed = 0;
   pl->recv[0] = pl->recv[1] = nullptr; pl->p2p = 0; pl->p2p_cur = 0; pl->recv_bytes = 0;
   pl->ring = nullptr; pl->ring_bytes = 0; pl->ctr = nullptr; pl->ctr_count = 0; pl->ctr_C = -1;
   for (int b = 0; b < 2; ++b) for (int q = 0; q < 8; ++q) pl->peers[b][q] = nullptr;
@@ -1080,8 +1160,27 @@ int ffb_plan_create(ffb_plan** out, int ndim, const int64_t* n, int dtype, int k
 
 int ffb_plan_create_dist(ffb_plan** out, int ndim, const int64_t* n, int dtype, ffb_dist* dist, int nchunks) {
   FFB_REQUIRE(dist, FFB_EINVAL, "dist is NULL");
-  FFB_REQUIRE(ndim == 3, FFB_EUNSUPPORTED, "slab decomposition is implemented for 3-D r2c grids");
+  FFB_REQUIRE(ndim == 3 || ndim == 2, FFB_EUNSUPPORTED, "slab decomposition is implemented for 2-D and 3-D r2c grids");
   const int P = dist->nranks;
+  if (ndim == 2) {
+    // physical y-slabs <-> spectral kx-blocks (exec_dist2d)
+    FFB_REQUIRE(n[1] % P == 0 && (n[0] / 2) % P == 0, FFB_EUNSUPPORTED, "nx/2 and ny must be divisible by the number of ranks (%d)", P);
+    int rc = ffb_plan_create(out, ndim, n, dtype, FFB_R2C, 1, FFB_PLAN_DEFAULT);
+    if (rc) return rc;
+    ffb_plan* pl = *out;
+    bool ok = true;
+    if (dtype == FFB_F64) { auto* t0 = reinterpret_cast<DimTables<double>*>(pl->tables[0]); auto* t1 = reinterpret_cast<DimTables<double>*>(pl->tables[1]); ok = t0->tw && t1->pow2 && (t1->four || t1->tw); }
+    else { auto* t0 = reinterpret_cast<DimTables<float>*>(pl->tables[0]); auto* t1 = reinterpret_cast<DimTables<float>*>(pl->tables[1]); ok = t0->tw && t1->pow2 && (t1->four || t1->tw); }
+    const long long kb = n[0] / 2 / P;
+    if (!ok || !is_pow2((uint64_t)kb)) { ffb_plan_destroy(pl); *out = nullptr; return set_error(FFB_EUNSUPPORTED, "slab-decomposed 2-D plans need power-of-two sizes (nx/2/nranks too)"); }
+    pl->dist = dist;
+    pl->nyl = n[1] / P; pl->nzl = 1; pl->kb = kb;
+    pl->ws_bytes = (size_t)(kb + 1) * (size_t)n[1] * 2 * dtype_size(dtype);
+    char buf[96];
+    snprintf(buf, sizeof(buf), "slab2d[rank %d/%d, kx block %lld + 1] ", dist->rank, P, kb);
+    pl->desc += buf;
+    return FFB_OK;
+  }
   FFB_REQUIRE(n[1] % P == 0 && n[2] % P == 0, FFB_EUNSUPPORTED, "ny and nz must be divisible by the number of ranks (%d)", P);
   int rc = ffb_plan_create(out, ndim, n, dtype, FFB_R2C, 1, FFB_PLAN_DEFAULT);
   if (rc) return rc;
@@ -1113,6 +1212,7 @@ std::mutex g_recv_mu;   // plans may be created / destroyed from different host 
 
 int ffb_plan_dist_recv_buffers(ffb_plan* pl, void** buf0, void** buf1, size_t* bytes_each) {
   FFB_REQUIRE(pl && pl->dist && buf0 && buf1, FFB_EINVAL, "needs a slab-decomposed plan");
+  FFB_REQUIRE(pl->ndim == 3, FFB_EUNSUPPORTED, "peer-memory exchanges are implemented for 3-D slab plans (2-D plans exchange over NCCL)");
   if (!pl->recv[0]) {
     // room for the kx-padded blocked layout of the peer-store exchange (kx rounded up to whole 64-byte blocks)
     const size_t esz = 2 * dtype_size(pl->dtype);
@@ -1210,6 +1310,7 @@ int ffb_plan_describe(const ffb_plan* pl, char* buf, size_t buflen) {
 int ffb_fft_forward(ffb_plan* pl, const void* in, void* out) {
   FFB_REQUIRE(pl && in && out, FFB_EINVAL, "NULL argument");
   if (pl->kind == FFB_R2C) FFB_REQUIRE(in != out, FFB_EINVAL, "r2c transforms are out of place");
+  if (pl->dist && pl->ndim == 2) return pl->dtype == FFB_F64 ? exec_dist2d<double>(pl, in, out, -1) : exec_dist2d<float>(pl, in, out, -1);
   if (pl->dist) return pl->dtype == FFB_F64 ? exec_dist<double>(pl, in, out, -1) : exec_dist<float>(pl, in, out, -1);
   return pl->dtype == FFB_F64 ? exec<double>(pl, in, out, -1) : exec<float>(pl, in, out, -1);
 }
@@ -1217,6 +1318,7 @@ int ffb_fft_forward(ffb_plan* pl, const void* in, void* out) {
 static int exec_fused(ffb_plan* pl, const void* in, void* out, int dir, const ffb_fuse* fuse) {
   FFB_REQUIRE(pl && in && out && fuse, FFB_EINVAL, "NULL argument");
   FFB_REQUIRE(in != out, FFB_EINVAL, "fused transforms are out of place");
+  if (pl->dist && pl->ndim == 2) return pl->dtype == FFB_F64 ? exec_dist2d<double>(pl, in, out, dir, fuse) : exec_dist2d<float>(pl, in, out, dir, fuse);
   if (pl->dist) return pl->dtype == FFB_F64 ? exec_dist<double>(pl, in, out, dir, fuse) : exec_dist<float>(pl, in, out, dir, fuse);
   bool allp = true;
   for (int d = 0; d < pl->ndim; ++d) {
@@ -1233,6 +1335,7 @@ int ffb_fft_inverse_ex(ffb_plan* pl, const void* in, void* out, const ffb_fuse* 
 int ffb_fft_inverse(ffb_plan* pl, const void* in, void* out) {
   FFB_REQUIRE(pl && in && out, FFB_EINVAL, "NULL argument");
   if (pl->kind == FFB_R2C) FFB_REQUIRE(in != out, FFB_EINVAL, "c2r transforms are out of place");
+  if (pl->dist && pl->ndim == 2) return pl->dtype == FFB_F64 ? exec_dist2d<double>(pl, in, out, +1) : exec_dist2d<float>(pl, in, out, +1);
   if (pl->dist) return pl->dtype == FFB_F64 ? exec_dist<double>(pl, in, out, +1) : exec_dist<float>(pl, in, out, +1);
   return pl->dtype == FFB_F64 ? exec<double>(pl, in, out, +1) : exec<float>(pl, in, out, +1);
 }

@@ -57,6 +57,11 @@ struct Pow2Params {
   Fuse pro, epi;
   const T* rmul;                     // C2R_ROWS: real result multiplied by this real field (same layout as out)
   int rsq;                           // R2C_ROWS: the real input is squared on load (`@. c = c * c` folded into the transform)
+  // R2C_ROWS store / C2R_ROWS load of a half spectrum cut into blocks of 2^row_seg_shift wavenumbers (2-D slab decomposition: block q
+  // belongs to rank q; the Nyquist wavenumber N rides with the last block): element k lives at (k & mask) + (k >> shift)*stride,
+  // k = N at row_nyq.  row_seg = 0: plain contiguous half spectrum.
+  int row_seg, row_seg_mask, row_seg_shift;
+  long long row_seg_stride, row_nyq;
   int pf_ahead;                      // ROWS modes: prefetch the line this many tiles ahead into L2 (0 = off)
   int reverse;                       // walk tiles / slices backwards (snake ordering between consecutive passes: the tail
                                      // of what the previous kernel wrote is still in the 126 MB L2)
@@ -319,6 +324,11 @@ FFB_D void fft_pow2_tile(const Pow2Params<T>& p, const unsigned bx, const unsign
     }
   }
   cx<T> v[R];
+  // position of half-spectrum element k within its line (R2C_ROWS store, C2R_ROWS load): plain, or cut into per-rank blocks
+  auto rowpos = [&](int k) -> long long {
+    if (!p.row_seg) return (long long)k;
+    return k == N ? p.row_nyq : (long long)(k & p.row_seg_mask) + (long long)(k >> p.row_seg_shift) * p.row_seg_stride;
+  };
   // ---------------- L2 prefetch of the tile a later CTA on this SM will load (contiguous lines only) ----------------
   // The row kernels are latency-bound at 2-4 CTAs/SM (ncu: long_scoreboard); pulling the line `pf_ahead` tiles ahead into
   // L2 now turns its DRAM miss into an L2 hit when that CTA starts.
@@ -340,13 +350,13 @@ FFB_D void fft_pow2_tile(const Pow2Params<T>& p, const unsigned bx, const unsign
     const cx<T> wbase = load_tw<T, -1>(p.twr + t);
     // all loads of X[k] first, then the partners X[N-k] in batches: independent loads are in flight together
 #pragma unroll
-    for (int m = 0; m < R; ++m) v[m] = active ? ldc(in + (t + m * Tn)) : mk<T>(0, 0);
+    for (int m = 0; m < R; ++m) v[m] = active ? ldc(in + rowpos(t + m * Tn)) : mk<T>(0, 0);
     constexpr int CB = R < 8 ? R : 8;
     static_for<0, R / CB>([&](auto MB) {
       constexpr int m0 = decltype(MB)::value * CB;
       cx<T> bv[CB];
 #pragma unroll
-      for (int q = 0; q < CB; ++q) bv[q] = active ? ldc(in + (N - (t + (m0 + q) * Tn))) : mk<T>(0, 0);
+      for (int q = 0; q < CB; ++q) bv[q] = active ? ldc(in + rowpos(N - (t + (m0 + q) * Tn))) : mk<T>(0, 0);
       static_for<0, CB>([&](auto Q) {
         constexpr int m = m0 + decltype(Q)::value;
         const int k = t + m * Tn;
@@ -441,8 +451,8 @@ FFB_D void fft_pow2_tile(const Pow2Params<T>& p, const unsigned bx, const unsign
       const cx<T> s = v[m] + conj(zp), d = v[m] - conj(zp);
       const cx<T> x = half * (s + mul_mi(wk * d));
       if (active) {
-        stk(out + k, x, p.keep_out);
-        if (k == 0) stk(out + N, mk<T>(v[m].x - v[m].y, T(0)), p.keep_out);
+        stk(out + rowpos(k), x, p.keep_out);
+        if (k == 0) stk(out + rowpos(N), mk<T>(v[m].x - v[m].y, T(0)), p.keep_out);
       }
     });
   } else if constexpr (MODE == C2R_ROWS) {

@@ -301,20 +301,29 @@ int ffb_problem_create(ffb_problem** out, const ffb_problem_config* cfg) {
   p->nkr = p->n[0] / 2 + 1;
   // slab decomposition: spectral (nkr, ny/P, nz), physical (nx, ny, nz/P)
   const int P = cfg->dist ? cfg->dist->nranks : 1, rank = cfg->dist ? cfg->dist->rank : 0;
+  const bool dist2d = cfg->dist && cfg->ndim == 2;
   if (cfg->dist) {
-    if (cfg->ndim != 3 || !(cfg->calcN == FFB_CALCN_BURGERS3D || cfg->calcN == FFB_CALCN_ZERO || cfg->calcN == FFB_CALCN_CALLBACK)) {
+    const bool ok3 = cfg->ndim == 3 && (cfg->calcN == FFB_CALCN_BURGERS3D || cfg->calcN == FFB_CALCN_ZERO || cfg->calcN == FFB_CALCN_CALLBACK);
+    const bool ok2 = cfg->ndim == 2 && (cfg->calcN == FFB_CALCN_VORTICITY2D || cfg->calcN == FFB_CALCN_ZERO || cfg->calcN == FFB_CALCN_CALLBACK);
+    if (!ok3 && !ok2) {
       delete p;
-      return set_error(FFB_EUNSUPPORTED, "slab-decomposed problems: 3-D grids with the Burgers / zero / callback calcN");
+      return set_error(FFB_EUNSUPPORTED, "slab-decomposed problems: 3-D grids with the Burgers / zero / callback calcN, 2-D grids with the vorticity / zero / callback calcN");
     }
-    if (p->n[1] % P || p->n[2] % P) { delete p; return set_error(FFB_EUNSUPPORTED, "ny and nz must be divisible by the number of ranks"); }
+    if (cfg->ndim == 3 && (p->n[1] % P || p->n[2] % P)) { delete p; return set_error(FFB_EUNSUPPORTED, "ny and nz must be divisible by the number of ranks"); }
+    if (cfg->ndim == 2 && (p->n[1] % P || (p->n[0] / 2) % P)) { delete p; return set_error(FFB_EUNSUPPORTED, "nx/2 and ny must be divisible by the number of ranks"); }
   }
-  const long long nyl = p->n[1] / (cfg->dist ? P : 1), nzl = p->n[2] / (cfg->dist ? P : 1);
-  p->nspec = p->nkr * nyl * p->n[2];
-  p->nphys = p->n[0] * p->n[1] * nzl;
+  // 3-D: spectral (nkr, ny/P, nz), physical (nx, ny, nz/P).  2-D: spectral (kb + 1, ny) with kb = nx/(2P) -- the Nyquist column rides with
+  // the last rank, the extra column is zero padding elsewhere --, physical (nx, ny/P)
+  const long long kb = dist2d ? p->n[0] / 2 / P : 0;
+  const long long nk0 = dist2d ? kb + 1 : p->nkr;
+  const long long nyl = dist2d ? p->n[1] : p->n[1] / ((cfg->dist && !dist2d) ? P : 1);
+  const long long nzl = p->n[2] / ((cfg->dist && !dist2d) ? P : 1);
+  p->nspec = nk0 * nyl * p->n[2];
+  p->nphys = dist2d ? p->n[0] * (p->n[1] / P) : p->n[0] * p->n[1] * nzl;
   p->sbytes = (size_t)p->nspec * 2 * es; p->pbytes = (size_t)p->nphys * es; p->rbytes = (size_t)p->nspec * es;
   ffb_desc& D = p->desc;
   D.ndim = p->nd; D.dtype = p->dtype;
-  D.dims[0] = p->nkr; D.dims[1] = nyl; D.dims[2] = p->n[2]; D.dims[3] = 1;
+  D.dims[0] = nk0; D.dims[1] = nyl; D.dims[2] = p->n[2]; D.dims[3] = 1;
   // getaliasedwavenumbers (src/domains.jl:408-421), evaluated in Float64
   for (int d = 0; d < 3; ++d) { D.alias_lo[d] = 0; D.alias_hi[d] = 0; }
   if (cfg->aliased_fraction > 0) {
@@ -324,7 +333,14 @@ int ffb_problem_create(ffb_problem** out, const ffb_problem_config* cfg) {
       D.alias_hi[d] = d == 0 ? (int32_t)p->nkr : (int32_t)std::ceil(Rf * (double)p->n[d]);  // kralias = iL:nkr for the half spectrum
     }
   }
-  if (cfg->dist && D.alias_lo[1] > 0) {
+  if (dist2d && D.alias_lo[0] > 0) {
+    // kralias = iL:nkr intersected with this rank's kx block [rank*kb + 1, (rank+1)*kb], in local 1-based indices; the extra column
+    // (Nyquist on the last rank, zero padding elsewhere) is always inside the aliased range
+    const long long lo = std::max<long long>(D.alias_lo[0], rank * kb + 1);
+    D.alias_lo[0] = (int32_t)(lo <= (rank + 1) * kb ? lo - rank * kb : kb + 1);
+    D.alias_hi[0] = (int32_t)(kb + 1);
+  }
+  if (cfg->dist && !dist2d && D.alias_lo[1] > 0) {
     // lalias intersected with this rank's y-slab [rank*nyl + 1, (rank+1)*nyl], shifted to local 1-based indices
     const long long lo = std::max<long long>(D.alias_lo[1], rank * nyl + 1), hi = std::min<long long>(D.alias_hi[1], (rank + 1) * nyl);
     if (lo > hi) { D.alias_lo[1] = 0; D.alias_hi[1] = 0; }
@@ -337,10 +353,18 @@ int ffb_problem_create(ffb_problem** out, const ffb_problem_config* cfg) {
   p->l = p->m = nullptr;
   FFB_TRY(dalloc(p, &p->kr, (size_t)p->nkr * es, false));
   FFB_TRY(ffb_wavenumbers(p->kr, p->n[0], cfg->L[0], p->dtype, 1));
+  if (dist2d) {
+    // this rank's kx block followed by the Nyquist wavenumber (a harmless stand-in on the ranks whose extra column is padding)
+    void* krl = nullptr;
+    FFB_TRY(dalloc(p, &krl, (size_t)nk0 * es, false));
+    FFB_TRY(ffb_d2d(krl, reinterpret_cast<char*>(p->kr) + (size_t)rank * kb * es, (size_t)kb * es));
+    FFB_TRY(ffb_d2d(reinterpret_cast<char*>(krl) + (size_t)kb * es, reinterpret_cast<char*>(p->kr) + (size_t)(p->nkr - 1) * es, es));
+    p->kr = krl;
+  }
   if (p->nd >= 2) {
     FFB_TRY(dalloc(p, &p->l, (size_t)p->n[1] * es, false));
     FFB_TRY(ffb_wavenumbers(p->l, p->n[1], cfg->L[1], p->dtype, 0));
-    if (cfg->dist) p->l = reinterpret_cast<char*>(p->l) + (size_t)rank * nyl * es;   // this rank's slice of the y-wavenumbers
+    if (cfg->dist && !dist2d) p->l = reinterpret_cast<char*>(p->l) + (size_t)rank * nyl * es;   // this rank's slice of the y-wavenumbers
   }
   if (p->nd >= 3) { FFB_TRY(dalloc(p, &p->m, (size_t)p->n[2] * es, false)); FFB_TRY(ffb_wavenumbers(p->m, p->n[2], cfg->L[2], p->dtype, 0)); }
   p->Krsq = p->invKrsq = p->Ldense = p->filter = nullptr;

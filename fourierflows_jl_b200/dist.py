@@ -46,6 +46,41 @@ def spectral_slab(ah: np.ndarray, nranks: int, rank: int) -> np.ndarray:
     return np.asfortranarray(ah[:, lo:hi, ...])
 
 
+def spectral_slab_2d(ah: np.ndarray, nranks: int, rank: int) -> np.ndarray:
+    """Local spectral slab of a 2-D grid: the half spectrum (nx/2 + 1, ny) is cut along kx into blocks of kb = nx/(2P) wavenumbers;
+    every rank holds (kb + 1, ny): its block plus one extra column -- the Nyquist wavenumber on the last rank, zero padding elsewhere."""
+    nkr = ah.shape[0]
+    if (nkr - 1) % nranks != 0:
+        raise L.FFBError(L.FFB_EUNSUPPORTED, f"nx/2 = {nkr - 1} is not divisible by the number of ranks {nranks}")
+    kb = (nkr - 1) // nranks
+    out = np.zeros((kb + 1,) + ah.shape[1:], dtype=ah.dtype, order="F")
+    out[:kb] = ah[rank * kb:(rank + 1) * kb]
+    if rank == nranks - 1:
+        out[kb] = ah[nkr - 1]
+    return out
+
+
+def gather_spectral_2d(slabs, nranks: int) -> np.ndarray:
+    """inverse of `spectral_slab_2d`: the full half spectrum from the ranks' slabs (list indexed by rank)"""
+    kb = slabs[0].shape[0] - 1
+    return np.asfortranarray(np.concatenate([s[:kb] for s in slabs] + [slabs[-1][kb:kb + 1]], axis=0))
+
+
+def physical_slab_2d(a: np.ndarray, nranks: int, rank: int) -> np.ndarray:
+    lo, hi = slab_range(a.shape[1], nranks, rank)
+    return np.asfortranarray(a[:, lo:hi])
+
+
+def local_kx_alias_2d(kralias, nx: int, nranks: int, rank: int):
+    """`grid.kralias` (1-based inclusive iL:nkr) in the local indices of a 2-D spectral slab: the block's part of the range plus the
+    extra column (always aliased); None when aliased_fraction = 0"""
+    if kralias is None:
+        return None
+    kb = nx // 2 // nranks
+    lo = max(kralias[0], rank * kb + 1)
+    return ((lo - rank * kb) if lo <= (rank + 1) * kb else kb + 1, kb + 1)
+
+
 def exchange_bytes_per_rank(shape, nranks: int, itemsize: int) -> int:
     """Bytes each rank sends per 3-D transform: S/P * (P-1)/P."""
     nkr = shape[0] // 2 + 1
@@ -163,19 +198,24 @@ AUTOTUNE_LOG = []
 
 
 class DistPlan:
-    """Slab-decomposed `rfftplan` of a 3-D grid: `mul(out, a)` / `ldiv(out, ah)` on the local slabs."""
+    """Slab-decomposed `rfftplan` of a 2-D or 3-D grid: `mul(out, a)` / `ldiv(out, ah)` on the local slabs."""
 
     def __init__(self, shape, T, dist: Dist, nchunks: int = 0):
         self.shape = tuple(int(s) for s in shape)
         self.T = np.dtype(T)
         self.dist = dist
-        n = (C.c_int64 * 3)(*self.shape)
+        nd = len(self.shape)
+        n = (C.c_int64 * 3)(*self.shape, *([1] * (3 - nd)))
         h = C.c_void_p()
-        L.call("ffb_plan_create_dist", C.byref(h), 3, n, ffb_dtype(self.T), dist._h, nchunks)
+        L.call("ffb_plan_create_dist", C.byref(h), nd, n, ffb_dtype(self.T), dist._h, nchunks)
         self._h = h
         P = dist.nranks
-        self.physical_shape = (self.shape[0], self.shape[1], self.shape[2] // P)
-        self.spectral_shape = (self.shape[0] // 2 + 1, self.shape[1] // P, self.shape[2])
+        if nd == 2:   # physical y-slabs <-> spectral kx blocks (+ the Nyquist / padding column)
+            self.physical_shape = (self.shape[0], self.shape[1] // P)
+            self.spectral_shape = (self.shape[0] // 2 // P + 1, self.shape[1])
+        else:
+            self.physical_shape = (self.shape[0], self.shape[1], self.shape[2] // P)
+            self.spectral_shape = (self.shape[0] // 2 + 1, self.shape[1] // P, self.shape[2])
 
     def describe(self):
         buf = C.create_string_buffer(512)

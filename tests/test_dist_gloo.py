@@ -96,6 +96,43 @@ def _worker(rank, world, port, q):
         by = flat[(((kx // B) * ny + yy) * nzl + zl) * B + kx % B]                 # what the inverse y-pass loads: (nkr, ny, nzl)
         back = sfft.irfft(sfft.ifft(by, axis=1), n=nx, axis=0)
         assert np.linalg.norm(back - xl) / np.linalg.norm(xl) < 1e-13
+        # 2c. 2-D slab decomposition (csrc/fft_plan.cu::exec_dist2d): physical y-slabs, spectral kx blocks of kb = nx/(2P) wavenumbers
+        #     plus one extra column (Nyquist on the last rank, zero padding elsewhere); the x pass stores each line's half spectrum
+        #     block by block in destination-rank-major order [peer][kb + 1, ny_local]; equal blocks -> plain all-to-all, no pack
+        nx2, ny2 = 16, 12
+        x2 = np.asfortranarray(rng.standard_normal((nx2, ny2)))
+        ref2 = sfft.rfftn(x2, axes=(1, 0))
+        kb, nyl2 = nx2 // 2 // P, ny2 // P
+        xl2 = ff.physical_slab_2d(x2, P, rank)
+        a2 = sfft.rfft(xl2, axis=0)                                                # (nkr, nyl)
+        send2 = np.zeros((P, kb + 1, nyl2), dtype=complex)
+        for k in range(nx2 // 2 + 1):
+            qd, kk = (P - 1, kb) if k == nx2 // 2 else (k // kb, k % kb)          # Pow2Params::row_seg_* / row_nyq
+            send2[qd, kk, :] = a2[k, :]
+        inbox2 = [None] * P
+        for dst in range(P):
+            gathered = [None] * P
+            dist.all_gather_object(gathered, send2[dst])
+            if rank == dst:
+                inbox2 = gathered
+        slab = np.zeros((kb + 1, ny2), dtype=complex, order="F")
+        for s_ in range(P):
+            slab[:, s_ * nyl2:(s_ + 1) * nyl2] = inbox2[s_]                        # rows of sender s land at y = s*nyl + y_local
+        spec2 = sfft.fft(slab, axis=1)
+        want2 = ff.spectral_slab_2d(ref2, P, rank)
+        assert np.linalg.norm(spec2 - want2) / np.linalg.norm(ref2) < 1e-13
+        if rank != P - 1:
+            assert np.all(spec2[kb] == 0)                                          # padding column stays exactly zero
+        everyone = [None] * P
+        dist.all_gather_object(everyone, spec2)
+        assert np.linalg.norm(ff.gather_spectral_2d(everyone, P) - ref2) / np.linalg.norm(ref2) < 1e-13
+        kal = ff.getaliasedwavenumbers(nx2, nx2 // 2 + 1, 1 / 3)[1]               # kralias = iL:nkr
+        lk = ff.local_kx_alias_2d(kal, nx2, P, rank)
+        gmask = np.zeros(nx2 // 2 + 1, bool)
+        gmask[kal[0] - 1:kal[1]] = True
+        lmask = np.zeros(kb + 1, bool)
+        lmask[lk[0] - 1:lk[1]] = True
+        assert np.array_equal(lmask[:kb], gmask[rank * kb:(rank + 1) * kb]) and lmask[kb]
         # 3. alias ranges on the slab
         lal = ff.getaliasedwavenumbers(ny, ny // 2 + 1, 1 / 3)[0]
         loc = ff.local_alias_range(lal, ny, P, rank)

@@ -53,6 +53,35 @@ def test_single_rank_slab_plan_matches_oracle(ff, T, tol, nch):
     comm.close()
 
 
+@pytest.mark.parametrize("T,tol", [(np.float64, 1e-12), (np.float32, 1e-5)])
+@pytest.mark.parametrize("shape", [(64, 32), (256, 4096), (128, 8192)], ids=lambda s: "x".join(map(str, s)))
+def test_single_rank_2d_slab_plan_matches_oracle(ff, T, tol, shape):
+    """2-D slab decomposition with P = 1 (the same kernels: block-segmented half spectrum, padded (kb + 1, ny) slab; single-pass and
+    four-step y lines): transforms and the fused vorticity problem against the oracle"""
+    comm = ff.Dist(0, 1, ff.Dist.unique_id())
+    rng = np.random.default_rng(4)
+    x = np.asfortranarray(rng.standard_normal(shape).astype(T))
+    plan = ff.DistPlan(shape, T, comm)
+    assert "slab2d" in plan.describe()
+    xh = plan * ff.DevArray.from_numpy(x)
+    ref = fo.RfftPlan(shape, T) * x.astype(np.float64)
+    assert relerr(xh.to_numpy(), ff.spectral_slab_2d(ref, 1, 0)) <= tol
+    assert relerr(plan.solve(xh).to_numpy(), x) <= tol
+    for fused in (0, 1):
+        n = shape[0]
+        cp = ff.CProblem((n, n), 2 * np.pi, stepper="ETDRK4", dt=2e-3, calcN="vorticity2d", nu=1e-3, T=T, dist=comm, fused=fused)
+        ob = fo.TwoDNavierStokes.Problem(nx=n, nu=1e-3, dt=2e-3, stepper="ETDRK4", T=T)
+        z0 = fo.random_phase_field((n, n), 2 * np.pi, 8.0, slope=-1, seed=1234, T=T)
+        cp.set_physical(z0)
+        ob.grid.rfftplan.mul(ob.sol, z0)
+        cp.stepforward(2)
+        fo.stepforward(ob, 2)
+        assert relerr(cp.sol.to_numpy(), ff.spectral_slab_2d(ob.sol, 1, 0)) <= 2 * tol
+        cp.close()
+    del plan
+    comm.close()
+
+
 def test_unsupported_decompositions_fail_loudly(ff):
     comm = ff.Dist(0, 1, ff.Dist.unique_id())
     with pytest.raises(ff.FFBError):
