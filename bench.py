@@ -14,6 +14,8 @@ Workloads (`--workload`; one "step" = one `stepforward!` of the named stepper):
   c4                    : configs[3] -- ThreeDGrid 1024^3 Float64, FilteredRK4, strong scaling over N = 1/2/4/8.
   c5-lsrk54             : configs[4], LSRK54 -- ThreeDGrid 2048^3 Float32, strong scaling over N = 2/4/8.
   c2                    : configs[1] -- TwoDGrid 4096^2 Float64 rfft + 2 x (ik, irfft) derivative round trip (1 GPU).
+  c3-slab               : the C3 problem slab-decomposed over N GPUs (physical y-slabs <-> spectral kx blocks; north star: "2D grids beyond
+                          one GPU's HBM"), strong scaling.
 `value` is Gpt*steps/s (grid points x steps / s / 1e9) so that all N share one unit; `steps_per_s` is reported beside it.
 Prints ONE JSON line (rank 0).
 """
@@ -91,12 +93,18 @@ class Vorticity2D(Workload):
     dtype, T = "f64", np.float64
     key = "c3"
 
-    def __init__(self, n, world, stepper="ETDRK4"):
-        self.shape, self.world, self.stepper = (n, n), 1, stepper
+    def __init__(self, n, world, stepper="ETDRK4", slab=False):
+        self.shape, self.world, self.stepper = (n, n), (world if slab else 1), stepper
         self.name = (f"C3: 2-D vorticity {stepper} {n}^2 Float64 (TwoDGrid, aliased_fraction=1/3, nu={self.nu}, dt={self.dt}), "
                      "random-phase IC seed 1234")
-        self.parallelism = "single GPU" if world == 1 else f"{world} independent replicas"
-        self.replicas = world
+        self.decomposed = bool(slab) and world > 1
+        self.key = "c3-slab" if slab else "c3"
+        if self.decomposed:
+            self.parallelism = f"slab decomposition x{world}: physical y-slabs <-> spectral kx blocks, one NCCL all-to-all per 2-D transform"
+            self.replicas = 1
+        else:
+            self.parallelism = "single GPU" if world == 1 else f"{world} independent replicas"
+            self.replicas = world
 
     def bytes_per_step(self):
         n, es = self.shape[0], 8
@@ -105,16 +113,20 @@ class Vorticity2D(Workload):
         fft = P + 3 * S
         calcN = (S + R + 2 * S) + 3 * fft + 5 * P + 2 * fft + 3 * S      # prep (no zeta_h copy) + 3 irfft + products + 2 rfft + combine
         base = self.stepper.replace("Filtered", "")
-        return NCALC[base] * calcN + stage_bytes(self.stepper, S, R, R), fft, 0.0
+        w = self.world if self.decomposed else 1
+        nvlink = 5 * NCALC[base] * (S / w) * (w - 1) / w                  # five transforms per calcN!, one exchange each
+        return NCALC[base] * calcN + stage_bytes(self.stepper, S, R, R), fft, nvlink
 
     def make_gpu(self, ff, fo, rank, comm, shape=None, seed=None):
         shape = shape or self.shape
-        prob = ff.CProblem(shape, 2 * np.pi, stepper=self.stepper, dt=self.dt, calcN="vorticity2d", nu=self.nu, T=self.T, fused=FUSED)
-        prob.set_physical(fo.random_phase_field(shape, 2 * np.pi, self.K0 * shape[0] / self.shape[0], slope=-1.0, seed=(1234 + rank) if seed is None else seed))
+        prob = ff.CProblem(shape, 2 * np.pi, stepper=self.stepper, dt=self.dt, calcN="vorticity2d", nu=self.nu, T=self.T, fused=FUSED, dist=comm)
+        field = fo.random_phase_field(shape, 2 * np.pi, self.K0 * shape[0] / self.shape[0], slope=-1.0,
+                                      seed=(1234 + (0 if comm is not None else rank)) if seed is None else seed)
+        prob.set_physical(ff.physical_slab_2d(field, comm.nranks, comm.rank) if comm is not None else field)
         return prob
 
     def fft_plan(self, ff, L, comm):
-        return ff.Plan(self.shape, self.T, L.FFB_R2C)
+        return ff.DistPlan(self.shape, self.T, comm) if comm is not None else ff.Plan(self.shape, self.T, L.FFB_R2C)
 
     def cpu_sizes(self):
         return [self.shape, (4096, 4096), (2048, 2048), (1024, 1024)]
@@ -212,6 +224,8 @@ def make_workload(args, world):
         wl = "c3" if world == 1 else "c5"
     if wl == "c3":
         return Vorticity2D(args.n, world)
+    if wl == "c3-slab":
+        return Vorticity2D(args.n, world, slab=True)
     if wl == "c2":
         return DerivativeRoundTrip(args.n if args.n != 8192 else 4096, world)
     if wl == "c5":
@@ -400,6 +414,30 @@ def parity_probe(wl, ff, fo, rank, world, comm, all_reduce_sum):
     tol = 1e-12 if wl.T == np.float64 else 1e-5
     if wl.kind == "transform":
         return None
+    if wl.decomposed and len(wl.shape) == 2:
+        # 2-D slab decomposition: transforms and two steps of the benchmarked problem at 1024^2, global rel-L2 vs the oracle
+        shape = (1024, 1024)
+        P = world
+        rng = np.random.default_rng(98)
+        x = np.asfortranarray(rng.standard_normal(shape).astype(wl.T))
+        ref = fo.RfftPlan(shape, wl.T) * x.astype(np.float64)
+        plan = ff.DistPlan(shape, wl.T, comm)
+        xh = plan * ff.DevArray.from_numpy(ff.physical_slab_2d(x, P, rank))
+        r = ff.spectral_slab_2d(ref, P, rank)
+        n1, d1 = all_reduce_sum(float(np.sum(np.abs(xh.to_numpy() - r) ** 2))), all_reduce_sum(float(np.sum(np.abs(r) ** 2)))
+        back = plan.solve(xh).to_numpy() - ff.physical_slab_2d(x, P, rank)
+        n2, d2 = all_reduce_sum(float(np.sum(back ** 2))), all_reduce_sum(float(np.sum(ff.physical_slab_2d(x, P, rank) ** 2)))
+        del plan, xh
+        prob = wl.make_gpu(ff, fo, rank, comm, shape=shape, seed=1234)
+        oprob = wl.make_cpu(fo, shape)
+        prob.stepforward(2)
+        fo.stepforward(oprob, 2)
+        r = ff.spectral_slab_2d(oprob.sol, P, rank)
+        num, den = all_reduce_sum(float(np.sum(np.abs(prob.sol.to_numpy() - r) ** 2))), all_reduce_sum(float(np.sum(np.abs(r) ** 2)))
+        prob.close()
+        e_fft, e_step = max((n1 / d1) ** 0.5, (n2 / d2) ** 0.5), (num / den) ** 0.5
+        return {"grid": list(shape), "fft_rel_l2": e_fft, "step_rel_l2_after_2": e_step, "tol_per_step": tol, "exchange": "nccl",
+                "ok": bool(e_fft <= tol and e_step <= 2 * tol)}
     if not wl.decomposed:
         shape = (1024, 1024)
         prob = wl.make_gpu(ff, fo, 0, None, shape=shape, seed=1234)
@@ -587,7 +625,7 @@ def run_gpu(args):
     gpt = sps * wl.points() / 1e9
     hbm_ms = total_bytes / share / peak / 1e6
     nvl_ms = nvlink_bytes / NVLINK_GBS / 1e6
-    nfft = 2 * NCALC[wl.stepper.replace("Filtered", "")]
+    nfft = (2 if len(wl.shape) == 3 else 5) * NCALC[wl.stepper.replace("Filtered", "")]
     line = {
         "metric": ("ETDRK4 " if "ETDRK4" in wl.stepper else wl.stepper + " ") + METRIC, "value": gpt, "unit": "Gpt*steps/s", "steps_per_s": sps,
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -709,7 +747,7 @@ def exchange_desc(prob, world, wl):
     names = {"peer-store": "peer stores over NVLink fused into the FFT pass (blocked receive layout)",
              "copy-engine": "kx-chunked copy-engine pushes into IPC-mapped peer buffers over NVLink, overlapped with the neighbouring chunks' passes",
              "nccl": "chunked NCCL all-to-all"}
-    used = getattr(prob, "exchange", "nccl") if P2P else "nccl"
+    used = getattr(prob, "exchange", "nccl") if (P2P and len(wl.shape) == 3) else "nccl"
     import fourierflows_jl_b200 as ff
     tuned = [t for t in ff.dist.AUTOTUNE_LOG if tuple(t["shape"]) == tuple(wl.shape)][:1] if EXCHANGE == "auto" else []
     return {"used": used, "how": names.get(used, used), "requested": EXCHANGE, "autotune_ms_fwd_plus_inv": tuned[0]["ms"] if tuned else None}
@@ -721,7 +759,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="auto", choices=["auto", "c2", "c3", "c4", "c5", "c5-lsrk54"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "c2", "c3", "c3-slab", "c4", "c5", "c5-lsrk54"])
     ap.add_argument("--n", type=int, default=8192, help="C3 / C2 grid size per side (C2 default 4096)")
     ap.add_argument("--n3", type=int, default=2048, help="3-D grid size (C5: x and y; C4 default 1024)")
     ap.add_argument("--nz-per-gpu", type=int, default=256, help="C5 z-planes per GPU (weak scaling; 256 x 8 = 2048)")

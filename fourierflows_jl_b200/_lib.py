@@ -121,6 +121,14 @@ SIGNATURES = {
     "ffb_ew_mul_real": [_vp, _vp, _vp, _i, _i64],
     "ffb_ew_spectral_mul": [_vp, _vp, _d, _d, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _P(ffb_desc)],
     "ffb_parseval_sum": [_P(_d), _vp, _i, _i, _P(ffb_desc)],
+    "ffb_ew_mul": [_vp, _vp, _i, _vp, _i, _i, _i64],
+    "ffb_jacobianh": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "ffb_snapshot_create": [_P(_vp), _sz, _i],
+    "ffb_snapshot_destroy": [_vp],
+    "ffb_snapshot_begin": [_vp, _vp, _sz, _P(_i)],
+    "ffb_snapshot_wait": [_vp, _i, _P(_vp)],
+    "ffb_snapshot_ready": [_vp, _i, _P(_i)],
+    "ffb_snapshot_release": [_vp, _i],
     "ffb_problem_create": [_P(_vp), _P(ffb_problem_config)],
     "ffb_problem_destroy": [_vp],
     "ffb_problem_sol": [_vp, _P(_vp), _P(_i64)],

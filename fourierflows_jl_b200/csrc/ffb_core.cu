@@ -213,6 +213,91 @@ int ffb_host_free_pinned(void* p) {
   return FFB_OK;
 }
 
+// ---------------------------------------------------------------- asynchronous output path
+// `saveoutput(out)` (src/output.jl:61-79) downloads every field with `Array(data)`, a blocking copy that stalls the step loop.
+// A snapshot ring decouples it: ffb_snapshot_begin copies the field into a device staging buffer on the compute stream (HBM
+// speed, stream-ordered with the steps), then a dedicated copy stream moves it to pinned host memory while stepping continues;
+// ffb_snapshot_wait blocks only the writer.
+struct ffb_snapshot {
+  size_t bytes; int nbuf, next;
+  std::vector<void*> dev, host;
+  std::vector<cudaEvent_t> staged, landed;
+  std::vector<int> busy;
+  cudaStream_t copy_stream;
+};
+
+int ffb_snapshot_create(ffb_snapshot** out, size_t bytes, int nbuf) {
+  FFB_REQUIRE(out && bytes > 0 && nbuf >= 1 && nbuf <= 64, FFB_EINVAL, "bad argument");
+  *out = nullptr;
+  auto* s = new ffb_snapshot();
+  s->bytes = bytes; s->nbuf = nbuf; s->next = 0; s->copy_stream = nullptr;
+  s->dev.assign(nbuf, nullptr); s->host.assign(nbuf, nullptr); s->staged.assign(nbuf, nullptr); s->landed.assign(nbuf, nullptr); s->busy.assign(nbuf, 0);
+  *out = s;   // partially built objects are destroyed by the caller through ffb_snapshot_destroy
+  FFB_CUDA(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < nbuf; ++i) {
+    int rc = ffb_malloc(&s->dev[i], bytes);
+    if (rc) return rc;
+    FFB_CUDA(cudaMallocHost(&s->host[i], bytes));
+    FFB_CUDA(cudaEventCreateWithFlags(&s->staged[i], cudaEventDisableTiming));
+    FFB_CUDA(cudaEventCreateWithFlags(&s->landed[i], cudaEventDisableTiming));
+  }
+  return FFB_OK;
+}
+
+int ffb_snapshot_destroy(ffb_snapshot* s) {
+  if (!s) return FFB_OK;
+  if (s->copy_stream) cudaStreamSynchronize(s->copy_stream);
+  for (int i = 0; i < s->nbuf; ++i) {
+    if (s->dev[i]) cudaFree(s->dev[i]);
+    if (s->host[i]) cudaFreeHost(s->host[i]);
+    if (s->staged[i]) cudaEventDestroy(s->staged[i]);
+    if (s->landed[i]) cudaEventDestroy(s->landed[i]);
+  }
+  if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
+  delete s;
+  return FFB_OK;
+}
+
+int ffb_snapshot_begin(ffb_snapshot* s, const void* dev_src, size_t bytes, int* slot) {
+  FFB_REQUIRE(s && dev_src && slot, FFB_EINVAL, "NULL argument");
+  FFB_REQUIRE(bytes <= s->bytes, FFB_EINVAL, "snapshot of %zu bytes exceeds the ring's %zu", bytes, s->bytes);
+  const int i = s->next;
+  FFB_REQUIRE(!s->busy[i], FFB_EINVAL, "snapshot ring is full: ffb_snapshot_release slot %d first", i);
+  cudaStream_t st = current_stream();
+  FFB_REQUIRE(st, FFB_ECUDA, "no CUDA stream (no device?)");
+  FFB_CUDA(cudaMemcpyAsync(s->dev[i], dev_src, bytes, cudaMemcpyDeviceToDevice, st));   // ordered with the steps
+  FFB_CUDA(cudaEventRecord(s->staged[i], st));
+  FFB_CUDA(cudaStreamWaitEvent(s->copy_stream, s->staged[i], 0));
+  FFB_CUDA(cudaMemcpyAsync(s->host[i], s->dev[i], bytes, cudaMemcpyDeviceToHost, s->copy_stream));   // beside the next steps
+  FFB_CUDA(cudaEventRecord(s->landed[i], s->copy_stream));
+  s->busy[i] = 1;
+  s->next = (i + 1) % s->nbuf;
+  *slot = i;
+  return FFB_OK;
+}
+
+int ffb_snapshot_wait(ffb_snapshot* s, int slot, void** host_ptr) {
+  FFB_REQUIRE(s && host_ptr && slot >= 0 && slot < s->nbuf && s->busy[slot], FFB_EINVAL, "bad slot");
+  FFB_CUDA(cudaEventSynchronize(s->landed[slot]));
+  *host_ptr = s->host[slot];
+  return FFB_OK;
+}
+
+int ffb_snapshot_ready(ffb_snapshot* s, int slot, int* ready) {
+  FFB_REQUIRE(s && ready && slot >= 0 && slot < s->nbuf && s->busy[slot], FFB_EINVAL, "bad slot");
+  cudaError_t e = cudaEventQuery(s->landed[slot]);
+  if (e != cudaSuccess && e != cudaErrorNotReady) return set_error(FFB_ECUDA, "cudaEventQuery: %s", cudaGetErrorString(e));
+  if (e == cudaErrorNotReady) cudaGetLastError();
+  *ready = e == cudaSuccess;
+  return FFB_OK;
+}
+
+int ffb_snapshot_release(ffb_snapshot* s, int slot) {
+  FFB_REQUIRE(s && slot >= 0 && slot < s->nbuf, FFB_EINVAL, "bad slot");
+  s->busy[slot] = 0;
+  return FFB_OK;
+}
+
 int ffb_mem_info(size_t* free_b, size_t* total_b) {
   size_t f = 0, t = 0;
   FFB_CUDA(cudaMemGetInfo(&f, &t));

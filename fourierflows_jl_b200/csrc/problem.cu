@@ -271,6 +271,24 @@ static int step_once(ffb_problem* p) {
 
 extern "C" {
 
+// `jacobianh(a, b, grid)`, real fields (src/utils.jl:190-197), from fused transforms only
+int ffb_jacobianh(ffb_plan* plan, void* out, const void* a, const void* b, const void* kr, const void* l, void* sh, void* p1, void* p2) {
+  FFB_REQUIRE(plan && out && a && b && kr && l && sh && p1 && p2, FFB_EINVAL, "NULL argument");
+  int rc;
+  if ((rc = ffb_fft_forward(plan, b, sh))) return rc;                       // bh = rfft(b)
+  ffb_fuse f;
+  memset(&f, 0, sizeof(f));
+  f.cr = 0.0; f.ci = 1.0; f.l = l; f.mul = a;
+  if ((rc = ffb_fft_inverse_ex(plan, sh, p1, &f))) return rc;               // p1 = a .* irfft(im * l .* bh)   (= a .* by)
+  f.l = nullptr; f.kx = kr;
+  if ((rc = ffb_fft_inverse_ex(plan, sh, p2, &f))) return rc;               // p2 = a .* irfft(im * kr .* bh)  (= a .* bx)
+  if ((rc = ffb_fft_forward(plan, p1, sh))) return rc;                      // sh = rfft(a .* by)
+  memset(&f, 0, sizeof(f));
+  f.cr = 0.0; f.ci = -1.0; f.l = l;                                          // own term: -im * l .* rfft(a .* bx)
+  f.acc = sh; f.ar = 0.0; f.ai = 1.0; f.akx = kr;                            // accumulated term: +im * kr .* rfft(a .* by)
+  return ffb_fft_forward_ex(plan, p2, out, &f);
+}
+
 int ffb_problem_destroy(ffb_problem* p) {
   if (!p) return FFB_OK;
   ffb_sync();

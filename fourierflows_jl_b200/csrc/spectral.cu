@@ -221,6 +221,17 @@ __global__ void mul_real_kernel(T* out, const T* x, const T* y, long long n) {
   for (long long i = nv * V + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = x[i] * y[i];
 }
 
+template <typename T, int XC, int YC>
+__global__ void mul_any_kernel(void* out, const void* x, const void* y, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    if constexpr (XC && YC) reinterpret_cast<cx<T>*>(out)[i] = reinterpret_cast<const cx<T>*>(x)[i] * reinterpret_cast<const cx<T>*>(y)[i];
+    else if constexpr (XC) { const T r = reinterpret_cast<const T*>(y)[i]; const cx<T> c = reinterpret_cast<const cx<T>*>(x)[i]; reinterpret_cast<cx<T>*>(out)[i] = mk<T>(c.x * r, c.y * r); }
+    else if constexpr (YC) { const T r = reinterpret_cast<const T*>(x)[i]; const cx<T> c = reinterpret_cast<const cx<T>*>(y)[i]; reinterpret_cast<cx<T>*>(out)[i] = mk<T>(r * c.x, r * c.y); }
+    else reinterpret_cast<T*>(out)[i] = reinterpret_cast<const T*>(x)[i] * reinterpret_cast<const T*>(y)[i];
+  }
+}
+
 template <typename T> FFB_D T ipow(T v, int p) {  // p >= 1; `k^2` is `k*k` in Julia (literal_pow)
   T r = v;
   for (int q = 1; q < p; ++q) r = r * v;
@@ -418,6 +429,27 @@ int ffb_ew_mul_real(void* out, const void* x, const void* y, int dtype, int64_t 
   const unsigned blocks = (unsigned)std::min<long long>((n + 255) / 256, (long long)num_sms() * 16);
   if (dtype == FFB_F64) mul_real_kernel<double><<<blocks, 256, 0, s>>>((double*)out, (const double*)x, (const double*)y, n);
   else mul_real_kernel<float><<<blocks, 256, 0, s>>>((float*)out, (const float*)x, (const float*)y, n);
+  count_launch();
+  FFB_CHECK_LAUNCH();
+  return FFB_OK;
+}
+
+int ffb_ew_mul(void* out, const void* x, int xc, const void* y, int yc, int dtype, int64_t n) {
+  FFB_REQUIRE(out && x && y, FFB_EINVAL, "NULL array");
+  FFB_REQUIRE(dtype == FFB_F32 || dtype == FFB_F64, FFB_EINVAL, "bad dtype");
+  if (n <= 0) return FFB_OK;
+  if (!xc && !yc) return ffb_ew_mul_real(out, x, y, dtype, n);
+  cudaStream_t s = current_stream();
+  FFB_REQUIRE(s, FFB_ECUDA, "no CUDA stream (no device?)");
+  const unsigned blocks = (unsigned)std::min<long long>((n + 255) / 256, (long long)num_sms() * 16);
+#define FFB_MULANY(T)                                                                    \
+  do {                                                                                   \
+    if (xc && yc) mul_any_kernel<T, 1, 1><<<blocks, 256, 0, s>>>(out, x, y, n);          \
+    else if (xc) mul_any_kernel<T, 1, 0><<<blocks, 256, 0, s>>>(out, x, y, n);           \
+    else mul_any_kernel<T, 0, 1><<<blocks, 256, 0, s>>>(out, x, y, n);                   \
+  } while (0)
+  if (dtype == FFB_F64) FFB_MULANY(double); else FFB_MULANY(float);
+#undef FFB_MULANY
   count_launch();
   FFB_CHECK_LAUNCH();
   return FFB_OK;

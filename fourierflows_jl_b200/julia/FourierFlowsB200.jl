@@ -529,6 +529,44 @@ ldiv!(out::B200Array, p::B200Plan, ah::B200Array, f::FFBFuse) =
 mul!(out::B200Array, p::B200Plan, a::B200Array, f::FFBFuse) =
   (check(ccall((:ffb_fft_forward_ex, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{FFBFuse}), p.handle, a.ptr, out.ptr, Ref(f))); out)
 
+# ---------------------------------------------------------------- `jacobianh` (src/utils.jl:190-197) and the asynchronous output path
+function FourierFlows.jacobianh(a::B200Array{T,2}, b::B200Array{T,2}, g::TwoDGrid) where T<:AbstractFloat
+  out = B200Array{Complex{T}}(undef, g.nkr, g.nl); sh = similar(out); p1 = similar(a); p2 = similar(a)
+  check(ccall((:ffb_jacobianh, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+              g.rfftplan.handle, out.ptr, a.ptr, b.ptr, g.kr.ptr, g.l.ptr, sh.ptr, p1.ptr, p2.ptr))
+  return out
+end
+FourierFlows.jacobian(a::B200Array{T,2}, b::B200Array{T,2}, g::TwoDGrid) where T<:AbstractFloat = g.rfftplan \ FourierFlows.jacobianh(a, b, g)
+"`mul!(out, x, y)`: out = x .* y for same-shape real / complex device arrays"
+function mul!(out::B200Array{To}, x::B200Array{Tx}, y::B200Array{Ty}) where {To,Tx,Ty}
+  check(ccall((:ffb_ew_mul, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ptr{Cvoid}, Cint, Cint, Int64),
+              out.ptr, x.ptr, Tx <: Complex, y.ptr, Ty <: Complex, ffbtype(To), length(out)))
+  return out
+end
+
+# `saveoutput(out)` (src/output.jl:61-79) downloads with a blocking `Array(data)`; the snapshot ring stages the field on the device in
+# stream order and copies it to pinned host memory on its own stream: `slot = snapshot!(ring, a)` inside the step loop (non-blocking),
+# `h = wait(ring, slot, T, dims)` on the writer's side, `release!(ring, slot)` afterwards.
+mutable struct SnapshotRing; handle :: Ptr{Cvoid}; end
+function SnapshotRing(bytes::Integer, nbuf::Integer=2)
+  h = Ref{Ptr{Cvoid}}(C_NULL)
+  check(ccall((:ffb_snapshot_create, lib), Cint, (Ptr{Ptr{Cvoid}}, Csize_t, Cint), h, bytes, nbuf))
+  r = SnapshotRing(h[])
+  finalizer(x -> ccall((:ffb_snapshot_destroy, lib), Cint, (Ptr{Cvoid},), x.handle), r)
+  return r
+end
+function snapshot!(r::SnapshotRing, a::B200Array{T}) where T
+  slot = Ref{Cint}(-1)
+  check(ccall((:ffb_snapshot_begin, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Csize_t, Ptr{Cint}), r.handle, a.ptr, length(a) * sizeof(T), slot))
+  return slot[]
+end
+function Base.wait(r::SnapshotRing, slot::Integer, ::Type{T}, dims::Dims) where T
+  p = Ref{Ptr{Cvoid}}(C_NULL)
+  check(ccall((:ffb_snapshot_wait, lib), Cint, (Ptr{Cvoid}, Cint, Ptr{Ptr{Cvoid}}), r.handle, slot, p))
+  return unsafe_wrap(Array, Ptr{T}(p[]), dims)      # view of the pinned buffer, valid until release!
+end
+release!(r::SnapshotRing, slot::Integer) = check(ccall((:ffb_snapshot_release, lib), Cint, (Ptr{Cvoid}, Cint), r.handle, slot))
+
 # ---------------------------------------------------------------- C-driven loop (`ffb_step`): benchmarks, or user calcN! passed as @cfunction
 # typedef int (*ffb_calcN_fn)(void* N, const void* sol, double t, void* user)
 struct FFBProblemConfig

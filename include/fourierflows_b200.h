@@ -59,6 +59,7 @@ typedef struct {
 typedef struct ffb_plan ffb_plan;
 typedef struct ffb_problem ffb_problem;
 typedef struct ffb_dist ffb_dist;
+typedef struct ffb_snapshot ffb_snapshot;
 
 /* ---------------------------------------------------------------- runtime */
 const char* ffb_last_error(void);
@@ -86,6 +87,18 @@ int ffb_d2d(void* dev_dst, const void* dev_src, size_t bytes);
 int ffb_host_alloc_pinned(void** host_ptr, size_t bytes);
 int ffb_host_free_pinned(void* host_ptr);
 int ffb_mem_info(size_t* free_bytes, size_t* total_bytes);
+
+/* Asynchronous output path: `saveoutput` (src/output.jl:61-79) downloads every field with a blocking `Array(data)`.
+ * A snapshot ring of nbuf (device staging buffer, pinned host buffer) pairs decouples it from the step loop: ffb_snapshot_begin
+ * enqueues a device-to-device copy on the library stream (ordered with the steps) and the device-to-host copy on a dedicated copy
+ * stream; ffb_snapshot_wait blocks until that slot has landed and returns the pinned host pointer; ffb_snapshot_release frees the
+ * slot.  Decomposed fields: every rank snapshots its slab, the launcher gathers the host buffers on rank 0. */
+int ffb_snapshot_create(ffb_snapshot** snap, size_t bytes, int nbuf);
+int ffb_snapshot_destroy(ffb_snapshot* snap);
+int ffb_snapshot_begin(ffb_snapshot* snap, const void* dev_src, size_t bytes, int* slot);
+int ffb_snapshot_wait(ffb_snapshot* snap, int slot, void** host_ptr);
+int ffb_snapshot_ready(ffb_snapshot* snap, int slot, int* ready);
+int ffb_snapshot_release(ffb_snapshot* snap, int slot);
 
 /* ---------------------------------------------------------------- B2 FFT plan protocol
  * `plan_flows_rfft` / `plan_flows_fft` src/domains.jl:2-5, called from the grid constructors :86-87, :207-208,
@@ -227,6 +240,16 @@ int ffb_ew_mul_real(void* out, const void* x, const void* y, int dtype, int64_t 
  * accumulate != 0 adds into out; dealias != 0 zeroes the aliased box afterwards (desc alias ranges). */
 int ffb_ew_spectral_mul(void* out, const void* in, double ar, double ai, const void* kx, int px, const void* l, int py,
                         const void* m, int pz, const void* w, int accumulate, int dealias, const ffb_desc* desc);
+
+/* out = x * y with x real or complex and y real or complex arrays of the same shape (`a .* by` for complex fields in `jacobianh`,
+ * src/utils.jl:198-203; a real factor multiplies both parts, as Julia's real*complex does) */
+int ffb_ew_mul(void* out, const void* x, int x_complex, const void* y, int y_complex, int dtype, int64_t n);
+/* `jacobianh(a, b, grid)` for real fields on a TwoDGrid (src/utils.jl:190-197):
+ *   out = im*kr .* rfft(a .* irfft(im*l .* rfft(b))) - im*l .* rfft(a .* irfft(im*kr .* rfft(b)))
+ * as five transforms with every multiply folded into a pass (no elementwise kernel).  rfftplan: the grid's 2-D r2c plan; a, b: real
+ * (nx, ny); out, scratch_h: complex (nx/2+1, ny); scratch_p1, scratch_p2: real (nx, ny); kr, l: the grid's wavenumber vectors. */
+int ffb_jacobianh(ffb_plan* rfftplan, void* out, const void* a, const void* b, const void* kr, const void* l, void* scratch_h,
+                  void* scratch_p1, void* scratch_p2);
 
 /* ---------------------------------------------------------------- diagnostics (src/utils.jl:113-183) */
 /* `parsevalsum2(uh, grid)` / `parsevalsum(uh, grid)` partial: returns Sum over modes with the half-spectrum

@@ -25,7 +25,7 @@ __all__ = [
     "dealias", "makefilter_K", "makefilter", "Equation", "Clock", "Problem", "TimeStepper", "stepforward",
     "step_until", "getetdcoeffs", "getexpLs", "STEPPERS", "isexplicit", "cxtype", "fltype",
     "Diffusion", "RfftPlan", "FftPlan", "set_fft_workers", "zeros", "LSRK54_A", "LSRK54_B", "LSRK54_C",
-    "TwoDNavierStokes", "Burgers3D", "random_phase_field",
+    "TwoDNavierStokes", "Burgers3D", "random_phase_field", "jacobianh", "jacobian",
 ]
 
 _WORKERS = os.cpu_count() or 1
@@ -747,6 +747,25 @@ class Burgers3D:
         L = np.asfortranarray((T.type(-kappa) * grid.Krsq).astype(T))
         eqn = Equation(L, Burgers3D.calcN, grid)
         return Problem(eqn, stepper, dt, grid, vars, Burgers3D.Params(kappa), **stepperkwargs)
+
+
+def jacobianh(a, b, grid):
+    """src/utils.jl:190-205 on a TwoDGrid (real fields through the rfft plan, complex ones through the fft plan)."""
+    if not np.iscomplexobj(a):
+        bh = grid.rfftplan * b
+        bx = grid.rfftplan.solve((1j * grid.kr) * bh)
+        by = grid.rfftplan.solve((1j * grid.l) * bh)
+        return (1j * grid.kr) * (grid.rfftplan * (a * by)) - (1j * grid.l) * (grid.rfftplan * (a * bx))
+    bh = grid.fftplan * b
+    bx = grid.fftplan.solve((1j * grid.k) * bh)
+    by = grid.fftplan.solve((1j * grid.l) * bh)
+    return (1j * grid.k) * (grid.fftplan * (a * by)) - (1j * grid.l) * (grid.fftplan * (a * bx))
+
+
+def jacobian(a, b, grid):
+    """src/utils.jl:212-218."""
+    jh = jacobianh(a, b, grid)
+    return grid.fftplan.solve(jh) if np.iscomplexobj(a) else grid.rfftplan.solve(jh)
 
 
 def random_phase_field(shape, Lext, K0, slope=1.0, seed=1234, T=np.float64):

@@ -316,3 +316,19 @@ def test_diagnostic_decay_rk4():
     a0 = prob.sol[1]
     fo.stepforward(prob, 100)
     assert np.isclose(prob.sol[1], a0 * np.exp(-1.0 * prob.clock.t), rtol=1e-10)
+
+
+def test_jacobian_kats():
+    """test/runtests.jl:243-280 + test/test_utils.jl:99-103: J(a, a) = 0, J(sin1, sin2) and J(exp1, exp2) against the analytic
+    expressions on TwoDGrid(nx=64, Lx=2pi, ny=128, Ly=3pi), atol = nx*ny*10*eps"""
+    nx, ny, Lx, Ly = 64, 128, 2 * np.pi, 3 * np.pi
+    g = fo.TwoDGrid(nx=nx, Lx=Lx, ny=ny, Ly=Ly)
+    x, y = np.asarray(g.x).reshape(-1, 1), np.asarray(g.y).reshape(1, -1)
+    k0, l0 = 2 * np.pi / Lx, 2 * np.pi / Ly
+    k1, l1, k2, l2 = 2 * k0, 6 * l0, 3 * k0, -3 * l0
+    s1, s2 = np.asfortranarray(np.sin(k1 * x + l1 * y)), np.asfortranarray(np.sin(k2 * x + l2 * y))
+    e1, e2 = np.asfortranarray(np.exp(1j * (k1 * x + l1 * y))), np.asfortranarray(np.exp(1j * (k2 * x + l2 * y)))
+    atol = nx * ny * 10 * np.finfo(np.float64).eps
+    assert np.linalg.norm(fo.jacobian(s1, s1, g)) <= atol
+    assert np.linalg.norm(fo.jacobian(s1, s2, g) - (k1 * l2 - k2 * l1) * np.cos(k1 * x + l1 * y) * np.cos(k2 * x + l2 * y)) <= atol
+    assert np.linalg.norm(fo.jacobian(e1, e2, g) - (k2 * l1 - k1 * l2) * np.exp(1j * ((k1 + k2) * x + (l1 + l2) * y))) <= atol
