@@ -873,11 +873,14 @@ static int exec_dist(ffb_plan* pl, const void* in, void* out, int dir, const ffb
   const long long blk = nkr * nyl * nzl;         // complex elements exchanged with each peer
   const int nch = pl->nchunks;
   const long long zc = nzl / nch, sub = nkr * nyl * zc;
-  int rc = ensure_ws(pl, 3);
+  // scratch: the NCCL exchange needs three slab-sized arrays, the copy-engine exchange w0 / w1 / w2 as well; the peer-store exchange
+  // only one (forward: r2c output, inverse: y-pass output -- never live together), which is what lets 2048^3 LSRK54 fit two GPUs
+  const int nws = pl->p2p == 1 ? 1 : 3;
+  int rc = ensure_ws(pl, nws);
   if (rc) return rc;
   cx<T>* w0 = reinterpret_cast<cx<T>*>(pl->ws[0]);
-  cx<T>* w1 = reinterpret_cast<cx<T>*>(pl->ws[1]);
-  cx<T>* w2 = reinterpret_cast<cx<T>*>(pl->ws[2]);
+  cx<T>* w1 = reinterpret_cast<cx<T>*>(pl->ws[nws == 1 ? 0 : 1]);
+  cx<T>* w2 = reinterpret_cast<cx<T>*>(pl->ws[nws == 1 ? 0 : 2]);
   long double tot = (long double)pl->n[0] * ny * nz;
   const T inv = (T)(1.0L / tot);
   SegStride seg; seg.seg = (int)nyl; seg.stride = blk;
@@ -1266,6 +1269,13 @@ int ffb_plan_dist_set_exchange(ffb_plan* pl, int mode) {
     FFB_REQUIRE(pl->nyl % (pl->n[1] / 16) == 0 && pl->nzl % (pl->n[2] / 16) == 0, FFB_EUNSUPPORTED, "peer-store exchange needs at most 16 ranks");
   }
   pl->p2p = mode;
+  if (mode == FFB_EXCHANGE_PEER_STORE && (pl->ws[1] || pl->ws[2])) {
+    // the peer-store exchange needs one scratch array: give back what an earlier exchange (e.g. the plan-time measurement) allocated
+    cudaStream_t st = current_stream();
+    if (st) FFB_CUDA(cudaStreamSynchronize(st));
+    FFB_CUDA(cudaStreamSynchronize(pl->dist->comm_stream));
+    for (int i = 1; i < 3; ++i) { if (pl->ws[i]) cudaFree(pl->ws[i]); pl->ws[i] = nullptr; }
+  }
   static const char* names[3] = {"exchange=nccl ", "exchange=peer-store ", "exchange=copy-engine "};
   const size_t prev = pl->desc.find("exchange=");
   if (prev != std::string::npos) pl->desc.erase(prev);   // the description names the exchange in use, not the history

@@ -186,6 +186,7 @@ static int calcN_impl(ffb_problem* p, void* N, const void* sol, double t) {
       square_real_kernel<T><<<blocks, 256, 0, s>>>((T*)p->ph1, p->nphys);
       count_launch(); }
       FFB_CHECK_LAUNCH();
+      if (!p->sh1 && (rc = dalloc(p, &p->sh1, p->sbytes, true))) return rc;
       if ((rc = ffb_fft_forward(p->plan, p->ph1, p->sh1))) return rc;
       return ffb_ew_spectral_mul(N, p->sh1, 0.0, -0.5, p->kr, 1, nullptr, 0, nullptr, 0, nullptr, 0, 1, d);
     }
@@ -435,9 +436,10 @@ int ffb_problem_create(ffb_problem** out, const ffb_problem_config* cfg) {
   if (cfg->calcN == FFB_CALCN_VORTICITY2D) {
     FFB_TRY(dalloc(p, &p->sh1, p->sbytes, true)); FFB_TRY(dalloc(p, &p->sh2, p->sbytes, true));
     FFB_TRY(dalloc(p, &p->ph2, p->pbytes, true)); FFB_TRY(dalloc(p, &p->ph3, p->pbytes, true));
-  } else if (cfg->calcN == FFB_CALCN_DIFFUSION || cfg->calcN == FFB_CALCN_BURGERS3D) {
+  } else if (cfg->calcN == FFB_CALCN_DIFFUSION) {
     FFB_TRY(dalloc(p, &p->sh1, p->sbytes, true));
   }
+  // Burgers: the spectral scratch of the unfused form (rfft output before `-1/2 im kr` + dealias!) is allocated on first use
   FFB_TRY(ffb_sync());
 #undef FFB_TRY
   *out = p;

@@ -56,8 +56,8 @@ def main():
                 {"FFB_FOURSTEP_MIN": "1024"}, {"FFB_FOURSTEP_MIN": "1024", "FFB_L2FOUR": "0"}, {"FFB_FOURSTEP_MIN": "100000"}]
     if quick:
         cases = cases[:3]
-        cases = cases[:3] + [((1024, 1024, 256), f64), ((512, 512, 512), f64)]
-        variants = [{}, {"FFB_ROWS_R8": "0"}, {"FFB_L2FOUR": "1"}, {"FFB_L2FOUR": "1", "FFB_L2_ACQ": "0"}, {"FFB_FOURSTEP_MIN": "2048"}, {"FFB_FOURSTEP_MIN": "1024"}]
+        cases = [((2048, 2048, 256), f32), ((1024, 1024, 1024), f32), ((1024, 1024, 256), f64), ((2048, 2048), f64), ((4096, 4096), f32)]
+        variants = [{}, {"FFB_FOURSTEP_MIN": "2048"}, {"FFB_FOURSTEP_MIN": "1024"}, {"FFB_FOURSTEP_MIN": "2048", "FFB_L2FOUR": "1"}]
     for shape, T in cases:
         for v in variants:
             for k in KEYS:
