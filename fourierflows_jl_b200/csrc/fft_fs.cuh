@@ -23,6 +23,7 @@ struct FsParams {
   const cx<T>* twN;            // A: exp(-2 pi i q / N), q < N
   int twN_mask;                // N - 1
   typename Pow2Params<T>::Fuse hook;   // PRO (A) or EPI (B) operands; .w / .acc are indexed like the true array
+  DeadCols dead;               // forward transforms followed by dealias!: A skips tiles of aliased columns, B writes their zeros unread
 };
 
 struct FsTile {
@@ -51,6 +52,17 @@ FFB_D void fs_tile(const FsParams<T>& p, const cx<T>* pin, cx<T>* pout, const Fs
   const int w = tid & (W - 1);
   const int t = tid >> p.lgW;
   const bool active = w < tl.ncols;
+  if (cols_all_dead(p.dead, tl.line0, tl.ncols)) {   // uniform over the CTA
+    sched.before_store();
+    if constexpr (!IS_A) {
+      if (p.dead.on == 2 && active) {
+        cx<T>* out = pout + tl.out_off + w + (long long)t * p.out_es;
+#pragma unroll
+        for (int m = 0; m < R; ++m) stc(out + (long long)m * p.out_ms, mk<T>(0, 0));
+      }
+    }
+    return;
+  }
   cx<T> v[R];
   // ---------------- load ----------------
   const cx<T>* in = pin + tl.in_off + w + (long long)t * p.in_es;

@@ -147,7 +147,7 @@ static const void* rows_tw8_for(const void* tw) {
 // points own 32-64 columns and run near the HBM roofline).  FFB_FOURSTEP_MIN overrides (0 disables).
 template <typename T> static int fourstep_min() {
   if (const char* e = getenv("FFB_FOURSTEP_MIN")) { const int v = atoi(e); return v > 0 ? v : (1 << 30); }
-  return sizeof(T) == 8 ? 4096 : 8192;
+  return 4096;   // Float32: 4096^2 r2c 0.084 ms split against 0.094 ms single pass (profiles/r02_fft_sweep.log)
 }
 
 template <typename T>
@@ -307,6 +307,9 @@ struct SegStride { int seg = 0; long long stride = 0; };  // seg = 0: unsegmente
 // half spectrum of the next row pass cut into per-rank blocks (2-D slab decomposition; set around the call by exec_dist2d)
 struct RowSeg { int seg = 0; long long stride = 0, nyq = 0; };
 static thread_local RowSeg g_row_seg;
+// dealias-aware forward transforms: dead half-spectrum range of the next r2c pass / dead columns of the next strided pass (see DeadCols)
+static thread_local int g_row_dead_lo = 0, g_row_dead_hi = 0;
+static thread_local DeadCols g_dead = {0, 1, 0, 0, 0, 0};
 // two-level outer index (four-step sub-passes): blockIdx.y = o_lo + mod*o_hi -> o_lo*os + o_hi*os2
 struct Outer2 { int mod = 0; long long nhi = 1, in_os2 = 0, out_os2 = 0; };
 
@@ -321,6 +324,7 @@ static int pow2_pass(int N, int mode, int dir, const void* in, void* out, long l
   p.rsq = rsq;
   p.row_seg = g_row_seg.seg; p.row_seg_mask = g_row_seg.seg ? g_row_seg.seg - 1 : 0; p.row_seg_shift = g_row_seg.seg ? ilog2((uint64_t)g_row_seg.seg) : 0;
   p.row_seg_stride = g_row_seg.stride; p.row_nyq = g_row_seg.nyq;
+  p.row_dead_lo = g_row_dead_lo; p.row_dead_hi = g_row_dead_hi; p.dead = g_dead;
   // plain strided passes: lean kernel variant with host-computed element offsets (needs segment lengths that are multiples of N/R)
   long long lean_out_off[16] = {0};
   static int lean_env = -1;
@@ -433,6 +437,7 @@ static int lean_tile_pass(int N, int dir, int W, const cx<T>* in, long long in_t
                           const cx<T>* tw, cudaStream_t st, const typename Pow2Params<T>::Fuse* epi = nullptr) {
   Pow2Params<T> p;
   p.rsq = 0; p.row_seg = 0; p.row_seg_mask = 0; p.row_seg_shift = 0; p.row_seg_stride = 0; p.row_nyq = 0;
+  p.row_dead_lo = p.row_dead_hi = 0; p.dead = g_dead;
   const int R = pow2_points_per_thread(N), Tn = N / R;
   FFB_REQUIRE(R == 16 && Tn * W <= pow2_max_threads(sizeof(T)) && nouter <= 65535, FFB_EUNSUPPORTED,
               "blocked strided pass: line length %d with %d-wide tiles is outside the kernel range", N, W);
@@ -470,6 +475,7 @@ static void fs_params(FsParams<T>& p, int Nsub, long long in_es, long long out_e
   p.W = kFsThreads / Tn; p.lgW = ilog2((uint64_t)p.W);
   p.scale = scale; p.tw = tw; p.twN = nullptr; p.twN_mask = 0;
   p.hook.on = 0;
+  p.dead = g_dead;
 }
 
 // Stand-alone four-step sub-pass (two-kernel form; the fused form is l2four_pass).  part 1 = A, part 2 = B.
@@ -483,6 +489,7 @@ static int fs_pass(const DimTables<T>* tb, int part, long long inner, long long 
   if (is_a) {
     fs_params<T>(q.p, N1, (long long)N2 * inner, (long long)N2 * inner, T(1), tb->tw1);
     q.p.twN = tb->twN; q.p.twN_mask = N - 1;
+    if (q.p.dead.on) q.p.dead.on = 1;   // sub-pass A only ever skips
     q.in_os = inner; q.out_os = inner; q.mod = N2;
     FFB_REQUIRE(!epi, FFB_EINVAL, "internal: epilogue on the first four-step sub-pass");
     if (pro) { pro->idm = N2; pro->ido = 1; q.p.hook = *pro; }
@@ -535,6 +542,7 @@ static int l2four_pass(ffb_plan* pl, const DimTables<T>* tb, long long inner, lo
   q.a.out_es = (long long)N2 * Wc; q.a.out_ms = (long long)(N1 / fs_points_per_thread((int)sizeof(T))) * q.a.out_es;
   q.b.in_es = Wc; q.b.in_ms = (long long)(N2 / fs_points_per_thread((int)sizeof(T))) * q.b.in_es;
   q.a.twN = tb->twN; q.a.twN_mask = N - 1;
+  if (q.a.dead.on) q.a.dead.on = 1;   // sub-pass A only ever skips; B zero-fills when this is the transform's last pass
   if (pro) { pro->idm = N2; pro->ido = 1; q.a.hook = *pro; }
   if (epi) { epi->idm = N1; epi->ido = 1; q.b.hook = *epi; }
   FFB_REQUIRE(!(pro && epi), FFB_EINVAL, "internal: prologue and epilogue on one transform");
@@ -734,6 +742,20 @@ static int exec_pow2(ffb_plan* pl, const void* in, void* out, int dir, const ffb
     const T sc = (dir > 0 && i == n - 1) ? inv : T(1);
     g_pass_reverse = snake_enabled() ? (i & 1) : 0;
     g_pass_keep = (snake_enabled() && i + 1 < n) ? 1 : 0;
+    // forward transform followed by dealias!: the aliased columns are not stored by the x pass, skipped by intermediate strided
+    // passes and zero-filled, unread, by the last pass (FFB_DEAD_SKIP=0 disables)
+    g_row_dead_lo = g_row_dead_hi = 0;
+    g_dead = DeadCols{0, 1, 0, 0, 0, 0};
+    if (fuse && dir < 0 && fuse->dealias && env_int("FFB_DEAD_SKIP", 1)) {
+      if (op.kind == 1 && fuse->alias_lo[0] > 0) { g_row_dead_lo = fuse->alias_lo[0] - 1; g_row_dead_hi = fuse->alias_hi[0]; }
+      if (op.kind == 3) {
+        g_dead.on = (i == n - 1) ? 2 : 1;
+        g_dead.n0 = (int)e[0];
+        if (fuse->alias_lo[0] > 0) { g_dead.dlo = fuse->alias_lo[0] - 1; g_dead.dhi = fuse->alias_hi[0]; }
+        if (op.d == 2 && fuse->alias_lo[1] > 0) { g_dead.olo = fuse->alias_lo[1] - 1; g_dead.ohi = fuse->alias_hi[1]; }
+        if (op.part == 4 && i != n - 1) g_dead.on = 1;
+      }
+    }
     int rc;
     if (op.kind == 0) rc = pow2_pass<T>(tb0->N, C2C_ROWS, dir, s_, d_, 1, tb0->N, 0, 1, tb0->N, 0, rows, 1, sc, tb0->tw, nullptr, st);
     else if (op.kind == 1)
@@ -755,6 +777,8 @@ static int exec_pow2(ffb_plan* pl, const void* in, void* out, int dir, const ffb
                         reinterpret_cast<cx<T>*>(d_), dir, sc, st, pro, epi);
     }
     g_pass_reverse = 0; g_pass_keep = 0;
+    g_row_dead_lo = g_row_dead_hi = 0;
+    g_dead = DeadCols{0, 1, 0, 0, 0, 0};
     if (rc) return rc;
   }
   return FFB_OK;

@@ -28,6 +28,23 @@ namespace ffb {
 // the plain strided passes are instruction-issue bound, this variant executes ~30 % fewer instructions.
 enum FftMode { C2C_ROWS = 0, C2C_COLS = 1, R2C_ROWS = 2, C2R_ROWS = 3, C2C_COLS_TW = 4, C2C_COLS_LEAN = 5 };
 
+// Columns of a forward transform that `dealias!` zeroes afterwards (the aliased kx range, and for a pass whose columns are
+// (kx, ky) pairs the aliased ky range) need neither be stored, transformed nor exchanged: intermediate passes skip tiles made of
+// such columns only, the last pass writes their zeros without loading anything.  Column c: i0 = c % n0, other = c / n0;
+// dead iff i0 in [dlo, dhi) or other in [olo, ohi) (0-based, half open; dhi = 0 / ohi = 0: no range).
+struct DeadCols {
+  int on;        // 0 = off, 1 = skip all-dead tiles, 2 = final pass: all-dead tiles are zero-filled
+  int n0, dlo, dhi, olo, ohi;
+};
+FFB_D bool cols_all_dead(const DeadCols& d, long long first, int ncols) {
+  if (!d.on || ncols <= 0) return false;
+  const long long last = first + ncols - 1;
+  const long long r0 = first / d.n0, r1 = last / d.n0;
+  if (d.ohi > d.olo && r0 >= d.olo && r1 < d.ohi) return true;
+  if (d.dhi > d.dlo && r0 == r1) { const int a = (int)(first - r0 * d.n0), b = (int)(last - r0 * d.n0); return a >= d.dlo && b < d.dhi; }
+  return false;
+}
+
 template <typename T>
 struct Pow2Params {
   const void* in;
@@ -62,6 +79,8 @@ struct Pow2Params {
   // k = N at row_nyq.  row_seg = 0: plain contiguous half spectrum.
   int row_seg, row_seg_mask, row_seg_shift;
   long long row_seg_stride, row_nyq;
+  int row_dead_lo, row_dead_hi;      // R2C_ROWS: half-spectrum elements k in [lo, hi) are not stored (dealiased later; see DeadCols)
+  DeadCols dead;                     // strided modes: see DeadCols
   int pf_ahead;                      // ROWS modes: prefetch the line this many tiles ahead into L2 (0 = off)
   int reverse;                       // walk tiles / slices backwards (snake ordering between consecutive passes: the tail
                                      // of what the previous kernel wrote is still in the 126 MB L2)
@@ -323,6 +342,27 @@ FFB_D void fft_pow2_tile(const Pow2Params<T>& p, const unsigned bx, const unsign
       }
     }
   }
+  if constexpr (COLS) {
+    // dealias-aware forward transforms: a tile made of aliased columns only is skipped (intermediate pass) or zero-filled (last pass)
+    const long long first = (long long)bx * W;
+    if (cols_all_dead(p.dead, first, (int)min((long long)W, nlines - first))) {   // uniform over the CTA
+      if (p.dead.on == 2 && active) {
+        if constexpr (LEAN) {
+          const long long oo = (long long)by * p.out_os + (long long)bx * p.out_ts + w + (long long)t * p.out_es;
+#pragma unroll
+          for (int m = 0; m < R; ++m) stk(p.out_m[m] + oo, mk<T>(0, 0), p.keep_out);
+        } else {
+          cx<T>* out = reinterpret_cast<cx<T>*>(pout) + o_lo * p.out_os + o_hi * p.out_os2 + line * p.out_ls;
+#pragma unroll
+          for (int m = 0; m < R; ++m) {
+            const int i = t + m * Tn;
+            stc(out + (long long)(i & p.out_seg_mask) * p.out_es + (long long)(i >> p.out_seg_shift) * p.out_seg_stride, mk<T>(0, 0));
+          }
+        }
+      }
+      return;
+    }
+  }
   cx<T> v[R];
   // position of half-spectrum element k within its line (R2C_ROWS store, C2R_ROWS load): plain, or cut into per-rank blocks
   auto rowpos = [&](int k) -> long long {
@@ -451,8 +491,8 @@ FFB_D void fft_pow2_tile(const Pow2Params<T>& p, const unsigned bx, const unsign
       const cx<T> s = v[m] + conj(zp), d = v[m] - conj(zp);
       const cx<T> x = half * (s + mul_mi(wk * d));
       if (active) {
-        stk(out + rowpos(k), x, p.keep_out);
-        if (k == 0) stk(out + rowpos(N), mk<T>(v[m].x - v[m].y, T(0)), p.keep_out);
+        if (!(k >= p.row_dead_lo && k < p.row_dead_hi)) stk(out + rowpos(k), x, p.keep_out);
+        if (k == 0 && !(N >= p.row_dead_lo && N < p.row_dead_hi)) stk(out + rowpos(N), mk<T>(v[m].x - v[m].y, T(0)), p.keep_out);
       }
     });
   } else if constexpr (MODE == C2R_ROWS) {
