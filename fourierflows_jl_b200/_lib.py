@@ -45,7 +45,8 @@ class ffb_desc(C.Structure):
 class ffb_fuse(C.Structure):
     _fields_ = [("cr", C.c_double), ("ci", C.c_double), ("kx", C.c_void_p), ("l", C.c_void_p), ("m", C.c_void_p), ("w", C.c_void_p),
                 ("acc", C.c_void_p), ("ar", C.c_double), ("ai", C.c_double), ("akx", C.c_void_p), ("al", C.c_void_p), ("am", C.c_void_p),
-                ("dealias", C.c_int), ("alias_lo", C.c_int32 * 3), ("alias_hi", C.c_int32 * 3), ("mul", C.c_void_p), ("square_input", C.c_int)]
+                ("dealias", C.c_int), ("alias_lo", C.c_int32 * 3), ("alias_hi", C.c_int32 * 3), ("mul", C.c_void_p), ("square_input", C.c_int),
+                ("galias_lo", C.c_int32 * 3), ("galias_hi", C.c_int32 * 3)]
 
 
 CALCN_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p)

@@ -35,6 +35,9 @@ enum FftMode { C2C_ROWS = 0, C2C_COLS = 1, R2C_ROWS = 2, C2R_ROWS = 3, C2C_COLS_
 struct DeadCols {
   int on;        // 0 = off, 1 = skip all-dead tiles, 2 = final pass: all-dead tiles are zero-filled
   int n0, dlo, dhi, olo, ohi;
+  // blocked passes of the slab decomposition (C2C_COLS_LEAN): outer slices `by` in [bylo, byhi) are dead; output elements whose
+  // transform index is in [tlo, thi) are not stored (the pass that feeds the exchange does not send aliased modes)
+  int bylo, byhi, tlo, thi;
 };
 FFB_D bool cols_all_dead(const DeadCols& d, long long first, int ncols) {
   if (!d.on || ncols <= 0) return false;
@@ -345,7 +348,8 @@ FFB_D void fft_pow2_tile(const Pow2Params<T>& p, const unsigned bx, const unsign
   if constexpr (COLS) {
     // dealias-aware forward transforms: a tile made of aliased columns only is skipped (intermediate pass) or zero-filled (last pass)
     const long long first = (long long)bx * W;
-    if (cols_all_dead(p.dead, first, (int)min((long long)W, nlines - first))) {   // uniform over the CTA
+    if (cols_all_dead(p.dead, first, (int)min((long long)W, nlines - first)) ||
+        (LEAN && p.dead.on && (int)by >= p.dead.bylo && (int)by < p.dead.byhi)) {   // uniform over the CTA
       if (p.dead.on == 2 && active) {
         if constexpr (LEAN) {
           const long long oo = (long long)by * p.out_os + (long long)bx * p.out_ts + w + (long long)t * p.out_es;
@@ -535,6 +539,12 @@ FFB_D void fft_pow2_tile(const Pow2Params<T>& p, const unsigned bx, const unsign
           T fr = fr0, fi = fi0;
           if (h.kt) { const T q = __ldg(h.kt + it); fr *= q; fi *= q; }
           stk(p.out_m[m] + oo, dead ? mk<T>(0, 0) : mk<T>(fr, fi) * (sc * v[m]), p.keep_out);
+        }
+      } else if (p.dead.on && p.dead.thi > p.dead.tlo) {
+#pragma unroll
+        for (int m = 0; m < R; ++m) {
+          const int it = t + m * Tn;
+          if (!(it >= p.dead.tlo && it < p.dead.thi)) stk(p.out_m[m] + oo, sc * v[m], p.keep_out);
         }
       } else if (sc != T(1)) {
 #pragma unroll

@@ -75,6 +75,7 @@ using namespace ffb;
 struct ffb_problem {
   ffb_problem_config cfg;
   ffb_desc desc;
+  int32_t galias_lo[3], galias_hi[3];   // global alias ranges (desc holds this rank's local ones on slab-decomposed problems)
   int nd, dtype;
   long long n[3], nkr, nspec, nphys;
   size_t sbytes, pbytes, rbytes;  // complex spectral array, real physical array, real spectral-shaped array
@@ -137,7 +138,12 @@ static int calcN_impl(ffb_problem* p, void* N, const void* sol, double t) {
         if ((rc = ffb_fft_inverse_ex(p->plan, sol, p->ph1, &f))) return rc;
         f.ci = -1.0; f.l = nullptr; f.kx = p->kr;
         if ((rc = ffb_fft_inverse_ex(p->plan, sol, p->ph2, &f))) return rc;
-        if ((rc = ffb_fft_forward(p->plan, p->ph1, p->sh1))) return rc;
+        // uh = rfft(u*zeta) is only ever read as the accumulated operand of the dealiased transform below, which never loads it
+        // inside the alias box: that box is don't-care here (dealias = 2), its columns are neither stored nor transformed
+        memset(&f, 0, sizeof(f));
+        f.cr = 1.0; f.dealias = d->alias_lo[0] > 0 ? 2 : 0;
+        for (int q = 0; q < 3; ++q) { f.alias_lo[q] = d->alias_lo[q]; f.alias_hi[q] = d->alias_hi[q]; }
+        if ((rc = ffb_fft_forward_ex(p->plan, p->ph1, p->sh1, &f))) return rc;
         memset(&f, 0, sizeof(f));
         f.cr = 0.0; f.ci = -1.0; f.l = p->l;                   // own term: -im * l * rfft(v*zeta)
         f.acc = p->sh1; f.ar = 0.0; f.ai = -1.0; f.akx = p->kr;   // accumulated term: -im * kr * uh
@@ -178,7 +184,7 @@ static int calcN_impl(ffb_problem* p, void* N, const void* sol, double t) {
         ffb_fuse f;
         memset(&f, 0, sizeof(f));
         f.cr = 0.0; f.ci = -0.5; f.kx = p->kr; f.dealias = 1; f.square_input = 1;
-        for (int q = 0; q < 3; ++q) { f.alias_lo[q] = d->alias_lo[q]; f.alias_hi[q] = d->alias_hi[q]; }
+        for (int q = 0; q < 3; ++q) { f.alias_lo[q] = d->alias_lo[q]; f.alias_hi[q] = d->alias_hi[q]; f.galias_lo[q] = p->galias_lo[q]; f.galias_hi[q] = p->galias_hi[q]; }
         return ffb_fft_forward_ex(p->plan, p->ph1, N, &f);
       }
       const unsigned blocks = (unsigned)std::min<long long>((p->nphys / 4 + 255) / 256, (long long)num_sms() * 16);
@@ -352,6 +358,7 @@ int ffb_problem_create(ffb_problem** out, const ffb_problem_config* cfg) {
       D.alias_hi[d] = d == 0 ? (int32_t)p->nkr : (int32_t)std::ceil(Rf * (double)p->n[d]);  // kralias = iL:nkr for the half spectrum
     }
   }
+  for (int d = 0; d < 3; ++d) { p->galias_lo[d] = D.alias_lo[d]; p->galias_hi[d] = D.alias_hi[d]; }
   if (dist2d && D.alias_lo[0] > 0) {
     // kralias = iL:nkr intersected with this rank's kx block [rank*kb + 1, (rank+1)*kb], in local 1-based indices; the extra column
     // (Nyquist on the last rank, zero padding elsewhere) is always inside the aliased range

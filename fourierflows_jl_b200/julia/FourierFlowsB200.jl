@@ -522,6 +522,7 @@ struct FFBFuse
   dealias :: Cint; alias_lo :: NTuple{3,Int32}; alias_hi :: NTuple{3,Int32}
   mul :: Ptr{Cvoid}
   square_input :: Cint
+  galias_lo :: NTuple{3,Int32}; galias_hi :: NTuple{3,Int32}
 end
 "`ldiv!(out, plan, ah, fuse)`: out = irfft(factor .* ah) [.* mul];  `mul!(outh, plan, a, fuse)`: outh = factor .* rfft(a) [+ g .* acc] [dealiased]"
 ldiv!(out::B200Array, p::B200Plan, ah::B200Array, f::FFBFuse) =

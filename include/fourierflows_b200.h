@@ -128,7 +128,9 @@ int ffb_fft_inverse(ffb_plan* plan, const void* in, void* out);
  * wavenumber factors and dealias (l = this rank's slice of the y wavenumbers, alias range 1 = the local range; no acc / w; NCCL and
  * peer-store exchanges).
  * Any vector / array pointer may be NULL (factor 1).  `w`, `acc` have the layout of the spectral array, `mul` of the
- * physical array.  dealias != 0 zeroes the alias box given by alias_lo/hi (as in ffb_desc). */
+ * physical array.  dealias = 1 zeroes the alias box given by alias_lo/hi (as in ffb_desc); dealias = 2 declares the box don't-care:
+ * the caller discards it (e.g. the array is only used as `acc` of a later dealiased forward_ex), so the transform may leave it
+ * unwritten.  Either way the aliased columns are not stored by the x pass and skipped by the strided passes. */
 typedef struct {
   double cr, ci;
   const void *kx, *l, *m, *w;
@@ -139,6 +141,9 @@ typedef struct {
   int32_t alias_lo[3], alias_hi[3];
   const void* mul;
   int square_input;   /* forward_ex: the real input is squared on load (`@. c = c * c` before `mul!`) */
+  /* slab-decomposed plans: the GLOBAL 1-based alias ranges (alias_lo/hi hold this rank's local ones); lets the pass that feeds the
+   * exchange skip the aliased modes instead of sending them.  All zero: unknown, everything is exchanged. */
+  int32_t galias_lo[3], galias_hi[3];
 } ffb_fuse;
 int ffb_fft_forward_ex(ffb_plan* plan, const void* in, void* out, const ffb_fuse* fuse);
 int ffb_fft_inverse_ex(ffb_plan* plan, const void* in, void* out, const ffb_fuse* fuse);

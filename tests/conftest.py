@@ -30,6 +30,12 @@ def pytest_collection_modifyitems(config, items):
     if HAVE_GPU is None:
         HAVE_GPU = _have_gpu()
     if HAVE_GPU:
+        # torch bundles its own NCCL: import it BEFORE libfourierflows_b200 dlopens the system libnccl.so.2 (the library then reuses
+        # the copy torch loaded; the other order makes a later `import torch` fail with an ImportError)
+        try:
+            import torch  # noqa: F401
+        except Exception:  # noqa: BLE001
+            pass
         return
     skip = pytest.mark.skip(reason="no CUDA device in this container")
     for item in items:
