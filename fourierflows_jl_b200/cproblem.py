@@ -57,6 +57,7 @@ class CProblem:
         cfg.kappa = kappa.ptr if kappa is not None else None
         cfg.coef_dtype = ffb_dtype(np.float64 if coef_dtype is None else coef_dtype)
         cfg.fused = int(fused)
+        self._fused = bool(fused)
         cfg.dist = dist._h if dist is not None else None
         h = C.c_void_p()
         L.call("ffb_problem_create", C.byref(h), C.byref(cfg))
@@ -78,7 +79,7 @@ class CProblem:
         from .dist import enable_p2p
         ph = C.c_void_p()
         L.call("ffb_problem_plan", self._h, C.byref(ph))
-        self.exchange = enable_p2p(ph, self.dist, mode, self.T, self.n)
+        self.exchange = enable_p2p(ph, self.dist, mode, self.T, self.n, prefer="peer-store" if self._fused else None)
         return self
 
     def device_bytes(self):

@@ -126,7 +126,7 @@ class Dist:
 EXCHANGE = {"nccl": 0, "peer-store": 1, "copy-engine": 2}
 
 
-def enable_p2p(plan_handle, dist: "Dist", mode: str = "peer-store", T=None, shape=None):
+def enable_p2p(plan_handle, dist: "Dist", mode: str = "peer-store", T=None, shape=None, prefer=None):
     """Exchange the IPC handles of a plan's two receive buffers over torch.distributed, hand the mapped peer pointers to
     the plan (`ffb_plan_dist_set_peers`) and select the exchange (`ffb_plan_dist_set_exchange`):
     "peer-store" = the pass before the exchange stores into the peers' buffers, "copy-engine" = chunked cudaMemcpyAsync pushes,
@@ -156,12 +156,12 @@ def enable_p2p(plan_handle, dist: "Dist", mode: str = "peer-store", T=None, shap
     L.call("ffb_sync")
     td.barrier()
     if mode == "auto":
-        return autotune_exchange(plan_handle, dist, T, shape)
+        return autotune_exchange(plan_handle, dist, T, shape, prefer=prefer)
     L.call("ffb_plan_dist_set_exchange", plan_handle, EXCHANGE[mode])
     return mode
 
 
-def autotune_exchange(plan_handle, dist: "Dist", T, shape, reps: int = 2):
+def autotune_exchange(plan_handle, dist: "Dist", T, shape, reps: int = 2, prefer=None, slack: float = 1.25):
     """Plan-time measurement (in the spirit of FFTW_MEASURE): time one forward + inverse transform of the plan's size with each
     exchange the plan supports and keep the fastest.  Collective; every rank takes the same decision (max over ranks)."""
     import time
@@ -188,9 +188,14 @@ def autotune_exchange(plan_handle, dist: "Dist", T, shape, reps: int = 2):
         td.all_gather_object(all_dt, dt)
         results[mode] = max(all_dt) / reps
     best = min(results, key=results.get)
+    # `prefer`: an exchange the caller gains more from than this plain-transform measurement shows (fused problems: only the
+    # peer-store / NCCL exchanges fold calcN!'s elementwise work into the passes and skip the aliased modes) wins unless it is
+    # more than `slack` times slower
+    if prefer in results and results[prefer] <= slack * results[best]:
+        best = prefer
     L.call("ffb_plan_dist_set_exchange", plan_handle, EXCHANGE[best])
     td.barrier()
-    AUTOTUNE_LOG.append({"shape": tuple(shape), "dtype": np.dtype(T).name, "ranks": P, "ms": {k: round(1e3 * v, 3) for k, v in results.items()}, "chosen": best})
+    AUTOTUNE_LOG.append({"shape": tuple(shape), "dtype": np.dtype(T).name, "ranks": P, "ms": {k: round(1e3 * v, 3) for k, v in results.items()}, "chosen": best, "preferred": prefer})
     return best
 
 
