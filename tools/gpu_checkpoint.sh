@@ -21,15 +21,17 @@ timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --
   python bench.py --steps 2 --warmup 1 --no-cpu-baseline > /dev/null 2>&1
 python tools/ncu_summarize.py launches $OUT/${R}_launches_raw.csv > $OUT/${R}_ncu_launches_n1.csv && head -12 $OUT/${R}_ncu_launches_n1.csv
 echo "== ncu --set full: one ETDRK4 step at 8192^2 F64 (fused calcN)"
-# skip the problem set-up and the first step (cold tables); capture the second step's kernels
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'fft_pow2_kernel|stage_kernel' --launch-skip 28 -c 28 \
+# skip the problem set-up (3 transform kernels) and the first step (64 launches, cold tables); capture the second step's 64 kernels
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'fft_pow2_kernel|stage_kernel|fs_pass_kernel' --launch-skip 67 -c 64 \
   -o $OUT/${R}_step python tools/run_step_once.py 8192 2 > /dev/null 2>&1
 ncu -i $OUT/${R}_step.ncu-rep --page raw --csv > $OUT/${R}_step_raw.csv 2>/dev/null
 python tools/ncu_summarize.py full $OUT/${R}_step_raw.csv > $OUT/${R}_ncu_full_step_kernels.csv && head -8 $OUT/${R}_ncu_full_step_kernels.csv
 rm -f $OUT/${R}_step.ncu-rep          # > 64 MiB reports are not copied back; the CSV exports are
 echo "== ncu --set full: Float32 3-D r2c passes (per-GPU share of C5)"
-timeout 400 ncu --set full --clock-control none -k regex:fft_pow2_kernel -c 6 -o $OUT/${R}_fft3d python tools/run_fft_once.py 2048x2048x256 f32 1 > /dev/null 2>&1
+timeout 400 ncu --set full --clock-control none -k regex:'fft_pow2_kernel|fs_pass_kernel' -c 6 -o $OUT/${R}_fft3d python tools/run_fft_once.py 2048x2048x256 f32 1 > /dev/null 2>&1
 ncu -i $OUT/${R}_fft3d.ncu-rep --page raw --csv > $OUT/${R}_fft3d_raw.csv 2>/dev/null
 python tools/ncu_summarize.py full $OUT/${R}_fft3d_raw.csv > $OUT/${R}_ncu_full_fft3d_f32_kernels.csv && cat $OUT/${R}_ncu_full_fft3d_f32_kernels.csv
 rm -f $OUT/${R}_fft3d.ncu-rep
+echo "== reference arm (driver flags)"; timeout 600 python bench.py --impl reference --steps 20 --warmup 5 > $OUT/${R}_bench_reference_n1.json 2> $OUT/${R}_bench_reference_n1.err; cut -c1-400 $OUT/${R}_bench_reference_n1.json
 echo "== transform sweep"; timeout 300 python tools/gpu_sweep.py > $OUT/${R}_fft_sweep.log 2>&1; grep -E "FAILURES|^time" $OUT/${R}_fft_sweep.log
+echo "== cuFFT reference times (torch.fft on the same box)"; timeout 200 python tools/cufft_times.py | tee $OUT/${R}_cufft_times.log

@@ -28,6 +28,23 @@ def prof_name(kernel: str) -> str:
         for r in m.group(4).split(",")[1:]:
             n *= int(r)
         return f"fft_c2c_cols_stream_{'f64' if m.group(1) == 'double' else 'f32'}_N{n}_{'fwd' if m.group(2) == '-1' else 'inv'}"
+    m = re.search(r"fs_pass_kernel<(float|double), (?:\(int\))?(-?1), (?:\(bool\))?(\d|true|false), (?:\(bool\))?(\d|true|false), (?:ffb::)?FsPlan<((?:\(int\))?\d+(?:, (?:\(int\))?\d+)+)>", kernel)
+    if m:
+        nums = [int(x) for x in re.findall(r"\d+", m.group(5))]
+        n = 1
+        for r in nums[1:]:
+            n *= r
+        is_a = m.group(3) in ("1", "true")
+        return f"fft_fs_{'a' if is_a else 'b'}_{'f64' if m.group(1) == 'double' else 'f32'}_N{n}_{'fwd' if m.group(2) == '-1' else 'inv'}"
+    m = re.search(r"fft_l2four_kernel<(float|double), (?:\(int\))?(-?1), (?:ffb::)?FsPlan<([^>]*)>, (?:ffb::)?FsPlan<([^>]*)>", kernel)
+    if m:
+        def prod(t):
+            v = [int(x) for x in re.findall(r"\d+", t)]
+            n = 1
+            for r in v[1:]:
+                n *= r
+            return n
+        return f"fft_l2four_{'f64' if m.group(1) == 'double' else 'f32'}_N{prod(m.group(3)) * prod(m.group(4))}_{'fwd' if m.group(2) == '-1' else 'inv'}"
     m = re.search(r"void (\w+(?:<.*>)?)\(", kernel)
     return (m.group(1) if m else kernel).replace(", ", "; ")
 
