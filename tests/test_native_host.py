@@ -25,5 +25,9 @@ def test_fft_design_model():
     for N, R, rad in [(64, 16, [16, 4]), (512, 16, [16, 16, 2]), (128, 16, [16, 8])]:
         x = rng.standard_normal(N) + 1j * rng.standard_normal(N)
         assert np.allclose(m.stockham(x, rad, R, -1), np.fft.fft(x), atol=1e-10)
-        w, rd = m.bank_conflicts(N, R, rad, 8, 16, 1)
+        for wordbytes in (8, 16):      # 8: Float32 complex; 16: Float64 complex, exchanged as whole words in one phase
+            w, rd = m.bank_conflicts(N, R, rad, wordbytes, 16, 1)
+            assert max(w + [rd]) == 1
+    for N, rad in [(4096, [16, 16, 16]), (8192, [16, 16, 8, 4]), (2048, [16, 16, 8])]:
+        w, rd = m.bank_conflicts(N, 16, rad, 16, 16, 1)
         assert max(w + [rd]) == 1

@@ -76,9 +76,9 @@ def c2r_pre(X):
 def bank_conflicts(N, R, radices, wordbytes, pad_every, pad_words=1, W=1):
     """Worst conflict degree of the scattered store of each non-final pass.  Element = one real of `wordbytes`
     (re/im split exchange).  A warp = 32 consecutive threads; a wavefront covers 128 bytes worth of lanes
-    (32 lanes for 4-byte words, 16 lanes for 8-byte words)."""
+    (32 lanes for 4-byte words, 16 for 8-byte words, 8 for the 16-byte complex words Float64 uses since round 2)."""
     T = N // R
-    lanes = 32 if wordbytes == 4 else 16
+    lanes = 128 // wordbytes          # a wavefront covers 128 bytes worth of lanes: 32 / 16 / 8 lanes for 4- / 8- / 16-byte words
     res = []
     Ns = 1
     for p, r in enumerate(radices[:-1]):
@@ -92,7 +92,7 @@ def bank_conflicts(N, R, radices, wordbytes, pad_every, pad_words=1, W=1):
                         j = t + b * T
                         idx = (j // Ns) * Ns * r + (j % Ns) + k * Ns
                         phys = idx + (idx // pad_every) * pad_words
-                        bank = (phys * wordbytes // 4) % 32 if wordbytes == 4 else (phys * 2) % 32
+                        bank = (phys * (wordbytes // 4)) % 32      # first 4-byte bank of the word; words are aligned to their size
                         banks[bank] = banks.get(bank, 0) + 1
                     worst = max(worst, max(banks.values()))
         res.append(worst)
@@ -105,7 +105,7 @@ def bank_conflicts(N, R, radices, wordbytes, pad_every, pad_words=1, W=1):
             for t in range(t0, min(t0 + lanes, T)):
                 idx = t + m * T
                 phys = idx + (idx // pad_every) * pad_words
-                bank = (phys * wordbytes // 4) % 32 if wordbytes == 4 else (phys * 2) % 32
+                bank = (phys * (wordbytes // 4)) % 32      # first 4-byte bank of the word; words are aligned to their size
                 banks[bank] = banks.get(bank, 0) + 1
             worst = max(worst, max(banks.values()))
     return res, worst
