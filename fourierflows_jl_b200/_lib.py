@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libfourierflows_b200.so")
+# FFB_LIB_PATH: another build of the same library (A/B timing of two builds on one box); the default is the in-tree build
+LIB_PATH = os.environ.get("FFB_LIB_PATH") or os.path.join(_HERE, "lib", "libfourierflows_b200.so")
 
 FFB_OK, FFB_EINVAL, FFB_EDOMAIN, FFB_ENOMEM, FFB_ECUDA, FFB_ENCCL, FFB_EUNSUPPORTED, FFB_ESTEPPER = 0, -1, -2, -3, -4, -5, -6, -7
 FFB_F32, FFB_F64 = 0, 1
@@ -91,6 +92,7 @@ SIGNATURES = {
     "ffb_fft_inverse": [_vp, _vp, _vp],
     "ffb_fft_forward_ex": [_vp, _vp, _vp, _P(ffb_fuse)],
     "ffb_fft_inverse_ex": [_vp, _vp, _vp, _P(ffb_fuse)],
+    "ffb_fft_inverse_multi": [_vp, _vp, _i, _P(_vp), _P(ffb_fuse)],
     "ffb_dist_unique_id": [_vp],
     "ffb_dist_init": [_P(_vp), _i, _i, _vp],
     "ffb_dist_destroy": [_vp],

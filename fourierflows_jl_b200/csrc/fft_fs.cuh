@@ -209,4 +209,37 @@ __global__ void __launch_bounds__(THREADS, MINB) fs_pass_kernel(const __grid_con
   PL::template tile<T, DIR, IS_A, HOOK, false, false>(q.p, q.in, q.out, tl, FsNoSched());
 }
 
+// Sub-pass A of several inverse transforms of the SAME spectral array that differ only in their prologue factor (calcN! of the 2-D
+// vorticity equation: zeta, u and v all come from `sol`).  One CTA runs the variants of its tile back to back: the first one pulls
+// the tile (and a dense factor shared between variants) from DRAM, the others find it in L1 / L2, so the input is read once
+// instead of `nv` times.  Tile geometry comes from q[0]; q[v] carries variant v's output and prologue.
+constexpr int kFsMaxVariants = 4;
+template <typename T>
+struct FsMultiLaunch {
+  FsLaunch<T> q[kFsMaxVariants];
+  int nv;
+};
+
+template <typename T, int DIR, class PL, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) fs_pass_multi_kernel(const __grid_constant__ FsMultiLaunch<T> mq) {
+  const FsLaunch<T>& q0 = mq.q[0];
+  FsTile tl;
+  tl.o_lo = (int)(blockIdx.y % (unsigned)q0.mod);
+  tl.o_hi = blockIdx.y / (unsigned)q0.mod;
+  tl.line0 = (long long)blockIdx.x * q0.p.W;
+  tl.ncols = (int)min((long long)q0.p.W, q0.nlines - tl.line0);
+  tl.in_off = tl.o_lo * q0.in_os + tl.o_hi * q0.in_os2 + tl.line0;
+  tl.out_off = tl.o_lo * q0.out_os + tl.o_hi * q0.out_os2 + tl.line0;
+  tl.hook_off = tl.in_off;
+  // all but the last variant load with .cg (normal L2 priority: the tile is about to be read again), the last one streams (.cs)
+#pragma unroll 1
+  for (int v = 0; v + 1 < mq.nv; ++v) {
+    const FsLaunch<T>& q = mq.q[v];
+    PL::template tile<T, DIR, true, true, true, false>(q.p, q.in, q.out, tl, FsNoSched());
+    __syncthreads();   // the exchange buffer is reused: every gather of this variant is done
+  }
+  const FsLaunch<T>& q = mq.q[mq.nv - 1];
+  PL::template tile<T, DIR, true, true, false, false>(q.p, q.in, q.out, tl, FsNoSched());
+}
+
 }  // namespace ffb

@@ -37,3 +37,6 @@ int l2four_call_double(int op, int N1, int N2, int dir, int hook, const void* pa
 // stand-alone sub-pass: is_a != 0: sub-pass A of length N (inter-pass twiddle, optional prologue), else sub-pass B (optional epilogue)
 int fs_call_float(int is_a, int N, int dir, int hook, const void* launch, int gx, int gy, size_t smem, void* stream);
 int fs_call_double(int is_a, int N, int dir, int hook, const void* launch, int gx, int gy, size_t smem, void* stream);
+// sub-pass A of up to kFsMaxVariants inverse transforms of one input (FsMultiLaunch): each variant has its own prologue and output
+int fs_multi_call_float(int N, int dir, const void* launch, int gx, int gy, size_t smem, void* stream);
+int fs_multi_call_double(int N, int dir, const void* launch, int gx, int gy, size_t smem, void* stream);

@@ -97,6 +97,31 @@ static int fs_dispatch(int is_a, int N, int dir, int hook, const FsLaunch<real_t
   return 1;
 }
 
+template <int N>
+static int fs_multi_one(int dir, const FsMultiLaunch<real_t>& mq, dim3 grid, size_t smem, cudaStream_t st) {
+  using PL = typename fs_plan_for<real_t, N>::type;
+  if (dir < 0) return set_error(FFB_EINVAL, "multi-variant sub-pass A: inverse transforms only");
+  auto kern = fs_pass_multi_kernel<real_t, 1, PL, kFsThreads, kMinB>;
+  static size_t configured = 0;
+  int rc = configure(kern, smem, configured);
+  if (rc) return rc;
+  kern<<<grid, kFsThreads, smem, st>>>(mq);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(FFB_ECUDA, "multi-variant four-step sub-pass launch failed: %s", cudaGetErrorString(e));
+  return FFB_OK;
+}
+
+static int fs_multi_dispatch(int N, int dir, const FsMultiLaunch<real_t>& mq, dim3 grid, size_t smem, cudaStream_t st) {
+  switch (N) {
+    case 32: return fs_multi_one<32>(dir, mq, grid, smem, st);
+    case 64: return fs_multi_one<64>(dir, mq, grid, smem, st);
+    case 128: return fs_multi_one<128>(dir, mq, grid, smem, st);
+    case 256: return fs_multi_one<256>(dir, mq, grid, smem, st);
+  }
+  return 1;
+}
+
 }  // namespace ffb
 
 #define FFB_CAT2(a, b) a##b
@@ -108,4 +133,8 @@ int FFB_CAT(l2four_call_, FFB_REAL)(int op, int N1, int N2, int dir, int hook, c
 int FFB_CAT(fs_call_, FFB_REAL)(int is_a, int N, int dir, int hook, const void* launch, int gx, int gy, size_t smem, void* stream) {
   return ffb::fs_dispatch(is_a, N, dir, hook, *reinterpret_cast<const ffb::FsLaunch<ffb::real_t>*>(launch), dim3(gx, gy, 1), smem,
                           reinterpret_cast<cudaStream_t>(stream));
+}
+int FFB_CAT(fs_multi_call_, FFB_REAL)(int N, int dir, const void* launch, int gx, int gy, size_t smem, void* stream) {
+  return ffb::fs_multi_dispatch(N, dir, *reinterpret_cast<const ffb::FsMultiLaunch<ffb::real_t>*>(launch), dim3(gx, gy, 1), smem,
+                                reinterpret_cast<cudaStream_t>(stream));
 }

@@ -80,6 +80,7 @@ struct ffb_plan {
   long long nc[3];    // complex array extents (nc[0] = n0/2+1 for R2C)
   void* tables[3];    // DimTables<T>*
   void* ws[3];        // scratch, allocated on first use
+  void* wsm[4];       // sub-pass A outputs of a multi-variant inverse transform (ffb_fft_inverse_multi), allocated on first use
   size_t ws_bytes;    // size of each scratch array
   std::string desc;
   ffb_dist* dist;     // non-NULL: slab-decomposed 3-D r2c plan (physical z-slabs <-> spectral y-slabs)
@@ -526,6 +527,57 @@ static int fs_pass(const DimTables<T>* tb, int part, long long inner, long long 
   return FFB_OK;
 }
 
+// Sub-pass A of `nv` inverse transforms of the same input (fft_fs.cuh: fs_pass_multi_kernel): variant v applies prologue pro[v] and
+// writes dst[v].
+template <typename T>
+static int fs_pass_multi(const DimTables<T>* tb, long long inner, long long outer, const cx<T>* src, int nv, cx<T>* const* dst,
+                         typename Pow2Params<T>::Fuse* pro, cudaStream_t st) {
+  const int N = tb->N, N1 = tb->N1, N2 = tb->N2;
+  FFB_REQUIRE(nv >= 1 && nv <= kFsMaxVariants, FFB_EINVAL, "1 to %d variants", kFsMaxVariants);
+  FsMultiLaunch<T> mq;
+  memset(&mq, 0, sizeof(mq));
+  mq.nv = nv;
+  double w_bytes = 0;
+  const T* seen_w[kFsMaxVariants] = {nullptr};
+  const double lines = (double)inner * (double)outer;
+  for (int v = 0; v < nv; ++v) {
+    FsLaunch<T>& q = mq.q[v];
+    fs_params<T>(q.p, N1, (long long)N2 * inner, (long long)N2 * inner, T(1), tb->tw1);
+    q.p.twN = tb->twN; q.p.twN_mask = N - 1;
+    q.p.dead.on = 0;
+    q.in_os = inner; q.out_os = inner; q.mod = N2;
+    q.in_os2 = inner * N; q.out_os2 = inner * N; q.nlines = inner;
+    pro[v].idm = N2; pro[v].ido = 1;
+    q.p.hook = pro[v];
+    bool dup = false;
+    for (int u = 0; u < v; ++u) dup = dup || seen_w[u] == pro[v].w;
+    seen_w[v] = pro[v].w;
+    if (pro[v].w && !dup) w_bytes += lines * N * sizeof(T);   // a dense factor shared by several variants comes from DRAM once
+    FFB_REQUIRE(!(pro[v].ko && outer > 65535 / N2), FFB_EUNSUPPORTED, "fused pass with more than 65535 outer slices");
+  }
+  const int W = mq.q[0].p.W;
+  const size_t smem = pow2_smem_bytes<T>(N1, W, C2C_COLS);
+  const long long gx = (inner + W - 1) / W;
+  FFB_REQUIRE(gx < (1ll << 31) && N2 <= 65535, FFB_EUNSUPPORTED, "too many lines for one launch");
+  char pname[64];
+  snprintf(pname, sizeof(pname), "fft_fs_am_%s_N%d", sizeof(T) == 8 ? "f64" : "f32", N1);
+  ProfScope ps(pname, lines * (1.0 + nv) * N * sizeof(cx<T>) + w_bytes);
+  const long long hchunk = std::max<long long>(1, 65535 / N2);
+  for (long long h0 = 0; h0 < outer; h0 += hchunk) {
+    const long long cnt = std::min<long long>(hchunk, outer - h0);
+    for (int v = 0; v < nv; ++v) {
+      FsLaunch<T>& q = mq.q[v];
+      q.in = src + h0 * q.in_os2; q.out = dst[v] + h0 * q.out_os2;
+      if (pro[v].w) q.p.hook.w = pro[v].w + h0 * q.in_os2;
+    }
+    int rc = sizeof(T) == 8 ? fs_multi_call_double(N1, +1, &mq, (int)gx, (int)(cnt * N2), smem, st)
+                            : fs_multi_call_float(N1, +1, &mq, (int)gx, (int)(cnt * N2), smem, st);
+    if (rc == 1) return set_error(FFB_EUNSUPPORTED, "no four-step sub-pass kernel for N = %d", N1);
+    if (rc) return rc;
+  }
+  return FFB_OK;
+}
+
 template <typename T>
 static int l2four_pass(ffb_plan* pl, const DimTables<T>* tb, long long inner, long long outer, const cx<T>* src, cx<T>* dst, int dir, T scale,
                        cudaStream_t st, typename Pow2Params<T>::Fuse* pro, typename Pow2Params<T>::Fuse* epi) {
@@ -693,7 +745,7 @@ static int c2c_dim(ffb_plan* pl, int d, const long long e[3], long long nb, cons
 // is scheduled over {IN (never written), OUT, WS0, WS1} so that the result lands in OUT and strictly out-of-place passes
 // (r2c, c2r, four-step B) never alias.
 template <typename T>
-static int exec_pow2(ffb_plan* pl, const void* in, void* out, int dir, const ffb_fuse* fuse = nullptr) {
+static int exec_pow2(ffb_plan* pl, const void* in, void* out, int dir, const ffb_fuse* fuse = nullptr, const void* a_done = nullptr) {
   cudaStream_t st = current_stream();
   FFB_REQUIRE(st, FFB_ECUDA, "no CUDA stream (no device?)");
   const int nd = pl->ndim;
@@ -723,6 +775,8 @@ static int exec_pow2(ffb_plan* pl, const void* in, void* out, int dir, const ffb
   }
   if (need_ws > 0) { int rc = ensure_ws(pl, need_ws); if (rc) return rc; }
   auto buf = [&](int b) -> void* { return b == IN ? const_cast<void*>(in) : b == OUT ? out : pl->ws[b - WS0]; };
+  // a_done: the first op (four-step sub-pass A, prologue included) was already run into that array by exec_pow2_multi
+  if (a_done) FFB_REQUIRE(n >= 2 && ops[0].kind == 3 && ops[0].part == 1, FFB_EINVAL, "internal: a_done without a four-step first pass");
   long double tot = 1;
   for (int d = 0; d < nd; ++d) tot *= (long double)pl->n[d];
   const T inv = (T)(1.0L / tot);
@@ -735,9 +789,9 @@ static int exec_pow2(ffb_plan* pl, const void* in, void* out, int dir, const ffb
     FFB_REQUIRE(dir > 0 ? ops[0].kind == 3 : ops[n - 1].kind == 3, FFB_EUNSUPPORTED, "no strided pass to fuse into");
   }
   const bool want_pro = fuse && dir > 0 && (fuse->kx || fuse->l || fuse->m || fuse->w || fuse->cr != 1.0 || fuse->ci != 0.0);
-  for (int i = 0; i < n; ++i) {
+  for (int i = a_done ? 1 : 0; i < n; ++i) {
     const Op& op = ops[i];
-    const void* s_ = buf(src[i]);
+    const void* s_ = (a_done && i == 1) ? a_done : buf(src[i]);
     void* d_ = buf(dst[i]);
     const T sc = (dir > 0 && i == n - 1) ? inv : T(1);
     g_pass_reverse = snake_enabled() ? (i & 1) : 0;
@@ -781,6 +835,42 @@ static int exec_pow2(ffb_plan* pl, const void* in, void* out, int dir, const ffb
     g_dead = DeadCols{0, 1, 0, 0, 0, 0, 0, 0, 0, 0};
     if (rc) return rc;
   }
+  return FFB_OK;
+}
+
+// `nv` inverse transforms of the same spectral array with different prologues.  When the first strided pass is a four-step pair, its
+// sub-pass A runs once for all variants (fs_pass_multi: the input is read from DRAM once) into per-variant scratch, and each variant
+// then finishes through the usual pass list.  Otherwise (or with FFB_MULTI_A=0): nv independent fused inverse transforms.
+template <typename T>
+static int exec_pow2_multi(ffb_plan* pl, const void* in, int nv, void* const* outs, const ffb_fuse* fuses) {
+  cudaStream_t st = current_stream();
+  FFB_REQUIRE(st, FFB_ECUDA, "no CUDA stream (no device?)");
+  const int nd = pl->ndim;
+  auto* tb = reinterpret_cast<DimTables<T>*>(pl->tables[nd - 1]);
+  const bool shared_a = nv >= 2 && nv <= kFsMaxVariants && pl->kind == FFB_R2C && nd >= 2 && pl->nbatch == 1 && tb->four &&
+                        !l2four_enabled(tb->N1, tb->N2) && env_int("FFB_MULTI_A", 1) != 0;
+  if (!shared_a) {
+    for (int v = 0; v < nv; ++v) {
+      int rc = exec_pow2<T>(pl, in, outs[v], +1, &fuses[v]);
+      if (rc) return rc;
+    }
+    return FFB_OK;
+  }
+  const long long e[3] = {pl->nc[0], pl->nc[1], pl->nc[2]};
+  const int d = nd - 1;
+  long long inner = 1;
+  for (int q = 0; q < d; ++q) inner *= e[q];
+  typename Pow2Params<T>::Fuse pro[kFsMaxVariants];
+  cx<T>* dst[kFsMaxVariants];
+  for (int v = 0; v < nv; ++v) {
+    if (!pl->wsm[v]) { int rc = ffb_malloc(&pl->wsm[v], pl->ws_bytes); if (rc) return rc; }
+    dst[v] = reinterpret_cast<cx<T>*>(pl->wsm[v]);
+    pro[v] = make_hook<T>(&fuses[v], d, nd, e, false);
+  }
+  int rc = fs_pass_multi<T>(tb, inner, 1, reinterpret_cast<const cx<T>*>(in), nv, dst, pro, st);
+  if (rc) return rc;
+  for (int v = 0; v < nv; ++v)
+    if ((rc = exec_pow2<T>(pl, in, outs[v], +1, &fuses[v], pl->wsm[v]))) return rc;
   return FFB_OK;
 }
 
@@ -1197,6 +1287,7 @@ int ffb_plan_create(ffb_plan** out, int ndim, const int64_t* n, int dtype, int k
   pl->recv[0] = pl->recv[1] = nullptr; pl->p2p = 0; pl->p2p_cur = 0; pl->recv_bytes = 0;
   pl->ring = nullptr; pl->ring_bytes = 0; pl->ctr = nullptr; pl->ctr_count = 0; pl->ctr_C = -1;
   for (int b = 0; b < 2; ++b) for (int q = 0; q < 8; ++q) pl->peers[b][q] = nullptr;
+  for (int i = 0; i < 4; ++i) pl->wsm[i] = nullptr;
   for (int d = 0; d < 3; ++d) { pl->n[d] = d < ndim ? n[d] : 1; pl->nc[d] = pl->n[d]; pl->tables[d] = nullptr; pl->ws[d] = nullptr; }
   if (kind == FFB_R2C) pl->nc[0] = pl->n[0] / 2 + 1;
   pl->ws_bytes = (size_t)pl->nc[0] * pl->nc[1] * pl->nc[2] * nbatch * 2 * dtype_size(dtype);
@@ -1338,6 +1429,7 @@ int ffb_plan_destroy(ffb_plan* pl) {
   if (!pl) return FFB_OK;
   if (pl->dtype == FFB_F64) free_tables<double>(pl); else free_tables<float>(pl);
   for (int i = 0; i < 3; ++i) cudaFree(pl->ws[i]);
+  for (int i = 0; i < 4; ++i) cudaFree(pl->wsm[i]);
   cudaFree(pl->ring); cudaFree(pl->ctr);
   if (pl->recv[0]) {
     std::lock_guard<std::mutex> lk(g_recv_mu);
@@ -1352,6 +1444,7 @@ int ffb_plan_workspace_bytes(const ffb_plan* pl, size_t* bytes) {
   FFB_REQUIRE(pl && bytes, FFB_EINVAL, "NULL argument");
   size_t b = 0;
   for (int i = 0; i < 3; ++i) if (pl->ws[i]) b += pl->ws_bytes;
+  for (int i = 0; i < 4; ++i) if (pl->wsm[i]) b += pl->ws_bytes;
   *bytes = b;
   return FFB_OK;
 }
@@ -1386,6 +1479,25 @@ static int exec_fused(ffb_plan* pl, const void* in, void* out, int dir, const ff
 
 int ffb_fft_forward_ex(ffb_plan* pl, const void* in, void* out, const ffb_fuse* fuse) { return exec_fused(pl, in, out, -1, fuse); }
 int ffb_fft_inverse_ex(ffb_plan* pl, const void* in, void* out, const ffb_fuse* fuse) { return exec_fused(pl, in, out, +1, fuse); }
+
+int ffb_fft_inverse_multi(ffb_plan* pl, const void* in, int n, void* const* outs, const ffb_fuse* fuses) {
+  FFB_REQUIRE(pl && in && outs && fuses, FFB_EINVAL, "NULL argument");
+  FFB_REQUIRE(n >= 1, FFB_EINVAL, "n = %d", n);
+  for (int v = 0; v < n; ++v) FFB_REQUIRE(outs[v] && outs[v] != in, FFB_EINVAL, "fused transforms are out of place");
+  bool allp = !pl->dist;
+  for (int d = 0; allp && d < pl->ndim; ++d) {
+    if (pl->dtype == FFB_F64) { auto* tb = reinterpret_cast<DimTables<double>*>(pl->tables[d]); allp = tb->pow2 && (tb->four || tb->tw); }
+    else { auto* tb = reinterpret_cast<DimTables<float>*>(pl->tables[d]); allp = tb->pow2 && (tb->four || tb->tw); }
+  }
+  if (!allp) {   // slab-decomposed or arbitrary-size plans: one fused inverse transform after the other
+    for (int v = 0; v < n; ++v) {
+      int rc = ffb_fft_inverse_ex(pl, in, outs[v], &fuses[v]);
+      if (rc) return rc;
+    }
+    return FFB_OK;
+  }
+  return pl->dtype == FFB_F64 ? exec_pow2_multi<double>(pl, in, n, outs, fuses) : exec_pow2_multi<float>(pl, in, n, outs, fuses);
+}
 
 int ffb_fft_inverse(ffb_plan* pl, const void* in, void* out) {
   FFB_REQUIRE(pl && in && out, FFB_EINVAL, "NULL argument");

@@ -117,16 +117,25 @@ __host__ __device__ constexpr int xpad_len(int n) { return n + (n >> 4) + 1; }
 // instructions of the re / im two-phase form round 1 used (ncu: the Float64 passes stall on barriers and the MIO queue, not on
 // DRAM).  The index pattern is conflict free for any word size: strided passes put adjacent columns (contiguous words) on a warp's
 // lanes; contiguous-line passes scatter with a stride of 17 words (the pad) in the first pass and to consecutive words afterwards.
+// -DFFB_ROWS_TWO_PHASE builds the round-1 form of the contiguous-line Float64 passes (re and im as 8-byte words in two phases) for
+// A/B timing of the two library builds on one box (FFB_LIB_PATH).
 template <typename T, bool COLS> struct xword;
+#ifdef FFB_ROWS_TWO_PHASE
+template <> struct xword<double, false> { using type = double; static constexpr int phases = 2; };
+template <> struct xword<double, true> { using type = double2; static constexpr int phases = 1; };
+#else
 template <bool COLS> struct xword<double, COLS> { using type = double2; static constexpr int phases = 1; };
+#endif
 template <bool COLS> struct xword<float, COLS> { using type = float2; static constexpr int phases = 1; };
 
 template <typename T, bool COLS, int PH> FFB_D typename xword<T, COLS>::type xget(const cx<T>& c) {
-  if constexpr (sizeof(T) == 8) return make_double2(c.x, c.y);
+  if constexpr (sizeof(T) == 8 && sizeof(typename xword<T, COLS>::type) == 8) return PH == 0 ? c.x : c.y;
+  else if constexpr (sizeof(T) == 8) return make_double2(c.x, c.y);
   else return make_float2(c.x, c.y);
 }
 template <typename T, bool COLS, int PH> FFB_D void xput(cx<T>& c, typename xword<T, COLS>::type w) {
-  c.x = w.x; c.y = w.y;
+  if constexpr (sizeof(T) == 8 && sizeof(typename xword<T, COLS>::type) == 8) { if (PH == 0) c.x = w; else c.y = w; }
+  else { c.x = w.x; c.y = w.y; }
 }
 
 template <int I, int N, typename F> FFB_D void static_for(F&& f) {
@@ -643,8 +652,13 @@ __global__ void __launch_bounds__(MAXT, MINB) fft_pow2_kernel(const __grid_const
 
 // shared-memory bytes needed by a launch with W lines per CTA (the r2c split step stages full complex values)
 template <typename T> constexpr size_t pow2_smem_bytes(int N, int W, int mode) {
+#ifdef FFB_ROWS_TWO_PHASE
+  const bool cols = (mode == C2C_COLS || mode == C2C_COLS_TW || mode == C2C_COLS_LEAN);
+  return (size_t)xpad_len(N) * W * 8 * (((mode == R2C_ROWS || cols) && sizeof(T) == 8) ? 2 : 1);
+#else
   (void)mode;
   return (size_t)xpad_len(N) * W * sizeof(cx<T>);   // one complex word per point (+ padding)
+#endif
 }
 
 }  // namespace ffb

@@ -131,13 +131,24 @@ static int calcN_impl(ffb_problem* p, void* N, const void* sol, double t) {
         //   zeta = irfft(sol);  u*zeta = irfft(im*l*invKrsq .* sol) .* zeta;  v*zeta = irfft(-im*kr*invKrsq .* sol) .* zeta
         //   uh = rfft(u*zeta);  N = dealias!(-im*kr .* uh - im*l .* rfft(v*zeta))
         ffb_fuse f;
-        memset(&f, 0, sizeof(f));
-        f.cr = 1.0;
-        if ((rc = ffb_fft_inverse(p->plan, sol, p->ph3))) return rc;
-        f.cr = 0.0; f.ci = 1.0; f.l = p->l; f.w = p->invKrsq; f.mul = p->ph3;
-        if ((rc = ffb_fft_inverse_ex(p->plan, sol, p->ph1, &f))) return rc;
-        f.ci = -1.0; f.l = nullptr; f.kx = p->kr;
-        if ((rc = ffb_fft_inverse_ex(p->plan, sol, p->ph2, &f))) return rc;
+        if (p->cfg.dist) {
+          memset(&f, 0, sizeof(f));
+          f.cr = 1.0;
+          if ((rc = ffb_fft_inverse(p->plan, sol, p->ph3))) return rc;
+          f.cr = 0.0; f.ci = 1.0; f.l = p->l; f.w = p->invKrsq; f.mul = p->ph3;
+          if ((rc = ffb_fft_inverse_ex(p->plan, sol, p->ph1, &f))) return rc;
+          f.ci = -1.0; f.l = nullptr; f.kx = p->kr;
+          if ((rc = ffb_fft_inverse_ex(p->plan, sol, p->ph2, &f))) return rc;
+        } else {
+          // the three inverse transforms share their input: one call, `sol` and invKrsq are read from DRAM once by the first sub-pass
+          ffb_fuse g[3];
+          memset(g, 0, sizeof(g));
+          g[0].cr = 1.0;
+          g[1].ci = 1.0; g[1].l = p->l; g[1].w = p->invKrsq; g[1].mul = p->ph3;
+          g[2].ci = -1.0; g[2].kx = p->kr; g[2].w = p->invKrsq; g[2].mul = p->ph3;
+          void* outs[3] = {p->ph3, p->ph1, p->ph2};
+          if ((rc = ffb_fft_inverse_multi(p->plan, sol, 3, outs, g))) return rc;
+        }
         // uh = rfft(u*zeta) is only ever read as the accumulated operand of the dealiased transform below, which never loads it
         // inside the alias box: that box is don't-care here (dealias = 2), its columns are neither stored nor transformed
         memset(&f, 0, sizeof(f));

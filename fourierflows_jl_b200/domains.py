@@ -89,6 +89,17 @@ class Plan:
         L.call("ffb_fft_inverse_ex", self._h, ah.ptr, out.ptr, C.byref(f))
         return out
 
+    def ldiv_multi(self, outs, ah: DevArray, variants):
+        """`outs[v] = irfft((coef_v * kx_v * l_v * m_v * w_v) .* ah) .* mul_v` for every keyword dict of `variants`, in order, sharing
+        the read of `ah` (ffb_fft_inverse_multi)."""
+        n = len(outs)
+        if n != len(variants):
+            raise ValueError("one keyword dict per output")
+        fuses = (L.ffb_fuse * n)(*[self._fuse(**kw) for kw in variants])
+        ptrs = (C.c_void_p * n)(*[o.ptr for o in outs])
+        L.call("ffb_fft_inverse_multi", self._h, ah.ptr, n, ptrs, fuses)
+        return outs
+
     def mul_ex(self, out: DevArray, a: DevArray, coef=1.0, kx=None, l=None, m=None, w=None, acc=None, acoef=0.0, akx=None, al=None, am=None,
                alias=None, square=False):
         """`out = dealias!((coef * kx * l * m * w) .* rfft(a) + (acoef * akx * al * am) .* acc)`; `alias` = per-dimension

@@ -147,6 +147,12 @@ typedef struct {
 } ffb_fuse;
 int ffb_fft_forward_ex(ffb_plan* plan, const void* in, void* out, const ffb_fuse* fuse);
 int ffb_fft_inverse_ex(ffb_plan* plan, const void* in, void* out, const ffb_fuse* fuse);
+/* n inverse_ex transforms of the SAME spectral array: outs[v] = irfft( F_v .* in ) .* mul_v, v = 0..n-1, evaluated in that order (so
+ * fuses[v].mul may be an earlier outs[u]).  calcN! of the 2-D vorticity equation takes zeta, u and v from one `sol`
+ * (three `ldiv!` calls on one input, src/diffusion.jl:137 being the single-field case); when the last dimension is long enough for the
+ * four-step split (>= 4096) its first sub-pass runs once for all variants and reads `in`, and a dense factor `w` the variants share,
+ * from DRAM once.  Costs n scratch arrays of the spectral size on first use.  Same results as n inverse_ex calls. */
+int ffb_fft_inverse_multi(ffb_plan* plan, const void* in, int n, void* const* outs, const ffb_fuse* fuses);
 
 /* ---------------------------------------------------------------- multi-GPU slab decomposition
  * No reference counterpart: FourierFlows.jl is single-device (README.md:58, docs/src/gpu.md:57); this is the new

@@ -240,6 +240,59 @@ def test_fused_transforms_match_unfused_reference_expressions(ff, shape, T, tol)
 
 
 @pytest.mark.parametrize("T,tol", [(np.float64, 1e-12), (np.float32, 1e-5)], ids=["f64", "f32"])
+@pytest.mark.parametrize("shape", [(64, 32), (64, 4096), (128, 8192), (16, 8, 4096), (30, 48)], ids=lambda s: "x".join(map(str, s)))
+def test_inverse_multi_shares_the_first_sub_pass_and_matches_separate_transforms(ff, shape, T, tol, monkeypatch):
+    """ffb_fft_inverse_multi (zeta, u*zeta, v*zeta of the vorticity calcN! from one `sol`): against the oracle expressions, and
+    bit-for-bit against separate ffb_fft_inverse_ex calls, for the shared four-step sub-pass (last dimension >= 4096, ragged column
+    tiles, 3-D), the single-pass fallback, FFB_MULTI_A=0, and -- error code -- arbitrary sizes."""
+    nd = len(shape)
+    G = {2: ff.TwoDGrid, 3: ff.ThreeDGrid}[nd]
+    OG = {2: fo.TwoDGrid, 3: fo.ThreeDGrid}[nd]
+    kw = dict(nx=shape[0], Lx=2 * np.pi, ny=shape[1], Ly=3 * np.pi, T=T)
+    if nd == 3:
+        kw.update(nz=shape[2], Lz=4.0)
+    g, og = G(ff.GPU(), **kw), OG(**kw)
+    rng = np.random.default_rng(77)
+    sh = (g.nkr,) + tuple(shape[1:])
+    cT = np.complex64 if T == np.float32 else np.complex128
+    ah = np.asfortranarray((rng.standard_normal(sh) + 1j * rng.standard_normal(sh)).astype(cT))
+    plan, oplan = g.rfftplan, og.rfftplan
+    dah = dev(ff, ah)
+    outs = [ff.DevArray(shape, T) for _ in range(3)]
+    variants = lambda: [dict(), dict(coef=1j, l=g.l, w=g.invKrsq, mul=outs[0]), dict(coef=-1j, kx=g.kr, w=g.invKrsq, mul=outs[0])]
+    if any(n & (n - 1) for n in shape):
+        with pytest.raises(ff.FFBError) as ei:
+            plan.ldiv_multi(outs, dah, variants())
+        assert ei.value.code == ff._lib.FFB_EUNSUPPORTED
+        return
+    zeta = oplan.solve(ah)
+    refs = [zeta, oplan.solve(((1j * og.l) * og.invKrsq) * ah) * zeta, oplan.solve(((-1j * og.kr) * og.invKrsq) * ah) * zeta]
+    got = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("FFB_MULTI_A", mode)
+        for o in outs:
+            o.fill_zero()
+        plan.ldiv_multi(outs, dah, variants())
+        got[mode] = [o.to_numpy() for o in outs]
+        for a, r in zip(got[mode], refs):
+            assert relerr(a, r) <= tol
+        assert np.array_equal(dah.to_numpy(), ah), "the input is preserved"
+    for a, b in zip(got["1"], got["0"]):
+        assert np.array_equal(a, b)
+    # separate calls
+    sep = [ff.DevArray(shape, T) for _ in range(3)]
+    plan.ldiv(sep[0], dah)
+    plan.ldiv_ex(sep[1], dah, coef=1j, l=g.l, w=g.invKrsq, mul=sep[0])
+    plan.ldiv_ex(sep[2], dah, coef=-1j, kx=g.kr, w=g.invKrsq, mul=sep[0])
+    for a, b in zip(got["1"], sep):
+        assert np.array_equal(a, b.to_numpy())
+    # twice on one plan (scratch reuse), two variants only
+    monkeypatch.setenv("FFB_MULTI_A", "1")
+    plan.ldiv_multi(outs[:2], dah, variants()[:2])
+    assert np.array_equal(outs[1].to_numpy(), got["1"][1])
+
+
+@pytest.mark.parametrize("T,tol", [(np.float64, 1e-12), (np.float32, 1e-5)], ids=["f64", "f32"])
 @pytest.mark.parametrize("shape", [(64, 1024), (66, 2048), (128, 4096), (32, 8192), (16, 16384), (32, 1024, 8), (16, 8, 2048), (8, 4096, 2)],
                          ids=lambda s: "x".join(map(str, s)))
 def test_fused_l2_four_step_matches_two_kernel_form_and_oracle(ff, shape, T, tol, monkeypatch):

@@ -21,14 +21,14 @@ timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --
   python bench.py --steps 2 --warmup 1 --no-cpu-baseline > /dev/null 2>&1
 python tools/ncu_summarize.py launches $OUT/${R}_launches_raw.csv > $OUT/${R}_ncu_launches_n1.csv && head -12 $OUT/${R}_ncu_launches_n1.csv
 echo "== ncu --set full: one ETDRK4 step at 8192^2 F64 (fused calcN)"
-# skip the problem set-up (3 transform kernels) and the first step (64 launches, cold tables); capture the second step's 64 kernels
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'fft_pow2_kernel|stage_kernel|fs_pass_kernel' --launch-skip 67 -c 64 \
+# skip the problem set-up (3 transform kernels) and the first step (56 launches, cold tables); capture the second step's 56 kernels
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'fft_pow2_kernel|stage_kernel|fs_pass' --launch-skip 59 -c 56 \
   -o $OUT/${R}_step python tools/run_step_once.py 8192 2 > /dev/null 2>&1
 ncu -i $OUT/${R}_step.ncu-rep --page raw --csv > $OUT/${R}_step_raw.csv 2>/dev/null
 python tools/ncu_summarize.py full $OUT/${R}_step_raw.csv > $OUT/${R}_ncu_full_step_kernels.csv && head -8 $OUT/${R}_ncu_full_step_kernels.csv
 rm -f $OUT/${R}_step.ncu-rep          # > 64 MiB reports are not copied back; the CSV exports are
 echo "== ncu --set full: Float32 3-D r2c passes (per-GPU share of C5)"
-timeout 400 ncu --set full --clock-control none -k regex:'fft_pow2_kernel|fs_pass_kernel' -c 6 -o $OUT/${R}_fft3d python tools/run_fft_once.py 2048x2048x256 f32 1 > /dev/null 2>&1
+timeout 400 ncu --set full --clock-control none -k regex:'fft_pow2_kernel|fs_pass' -c 6 -o $OUT/${R}_fft3d python tools/run_fft_once.py 2048x2048x256 f32 1 > /dev/null 2>&1
 ncu -i $OUT/${R}_fft3d.ncu-rep --page raw --csv > $OUT/${R}_fft3d_raw.csv 2>/dev/null
 python tools/ncu_summarize.py full $OUT/${R}_fft3d_raw.csv > $OUT/${R}_ncu_full_fft3d_f32_kernels.csv && cat $OUT/${R}_ncu_full_fft3d_f32_kernels.csv
 rm -f $OUT/${R}_fft3d.ncu-rep

@@ -36,6 +36,13 @@ def prof_name(kernel: str) -> str:
             n *= r
         is_a = m.group(3) in ("1", "true")
         return f"fft_fs_{'a' if is_a else 'b'}_{'f64' if m.group(1) == 'double' else 'f32'}_N{n}_{'fwd' if m.group(2) == '-1' else 'inv'}"
+    m = re.search(r"fs_pass_multi_kernel<(float|double), (?:\(int\))?(-?1), (?:ffb::)?FsPlan<((?:\(int\))?\d+(?:, (?:\(int\))?\d+)+)>", kernel)
+    if m:
+        nums = [int(x) for x in re.findall(r"\d+", m.group(3))]
+        n = 1
+        for r in nums[1:]:
+            n *= r
+        return f"fft_fs_am_{'f64' if m.group(1) == 'double' else 'f32'}_N{n}_{'fwd' if m.group(2) == '-1' else 'inv'}"
     m = re.search(r"fft_l2four_kernel<(float|double), (?:\(int\))?(-?1), (?:ffb::)?FsPlan<([^>]*)>, (?:ffb::)?FsPlan<([^>]*)>", kernel)
     if m:
         def prod(t):
