@@ -63,30 +63,66 @@ FFB_D void fs_tile(const FsParams<T>& p, const cx<T>* pin, cx<T>* pout, const Fs
     }
     return;
   }
+  if constexpr (HOOK && !IS_A) {
+    // the accumulated array is consumed after the transform: pull the live part of its tile towards L2 now, or its loads would be a
+    // second exposed DRAM round trip (one request per 128-byte line; a warp's lanes cover adjacent columns)
+    const typename Pow2Params<T>::Fuse& h = p.hook;
+    if (active && h.acc) {
+      const unsigned line = (unsigned)(tl.line0 + w);
+      unsigned ci0, cio;
+      col_coords(line, (unsigned)h.n0, ci0, cio);
+      const int i0 = (int)ci0;
+      const long long io = h.other_from_col == 1 ? (long long)cio : (h.other_from_col == 2 ? (long long)tl.o_lo : tl.o_hi);
+      const bool dead0 = h.dealias && ((h.lo0 > 0 && i0 >= h.lo0 - 1 && i0 < h.hi0) || (h.loo > 0 && io >= h.loo - 1 && io < h.hio));
+      if (!dead0) {
+        const cx<T>* ap = h.acc + tl.hook_off + w + (long long)t * p.out_es;
+#pragma unroll
+        for (int m = 0; m < R; ++m) {
+          const int it = h.idm * (t + m * Tn) + h.ido * tl.o_lo;
+          const cx<T>* a = ap + (long long)m * p.out_ms;
+          const bool live = !(h.dealias && h.lot > 0 && it >= h.lot - 1 && it < h.hit);
+          if (live && (w == 0 || (reinterpret_cast<uintptr_t>(a) & 127) < sizeof(cx<T>))) prefetch_l2(a);
+        }
+      }
+    }
+  }
   cx<T> v[R];
   // ---------------- load ----------------
   const cx<T>* in = pin + tl.in_off + w + (long long)t * p.in_es;
 #pragma unroll
   for (int m = 0; m < R; ++m) v[m] = active ? ldin<T, IN_CG>(in + (long long)m * p.in_ms) : mk<T>(0, 0);
   if constexpr (HOOK && IS_A) {
-    // prologue: (cr + i ci) * k0[i0] * kt[it] * ko[io] * w[.] * x, evaluated left to right like `im * l * invKrsq * sol`
+    // prologue: (cr + i ci) * k0[i0] * kt[it] * ko[io] * w[.] * x, evaluated left to right like `im * l * invKrsq * sol`.
+    // Every operand load is issued before anything is consumed (the pass is latency-bound: ncu long_scoreboard), and the column
+    // coordinates use 32-bit arithmetic (a 64-bit modulo is a subroutine call that the loads cannot be scheduled across).
     if (active) {
       const typename Pow2Params<T>::Fuse& h = p.hook;
-      const long long line = tl.line0 + w;
-      const int i0 = (int)(line % h.n0);
-      const long long io = h.other_from_col == 1 ? line / h.n0 : (h.other_from_col == 2 ? (long long)tl.o_lo : tl.o_hi);
+      const unsigned line = (unsigned)(tl.line0 + w);
       const T* wp = h.w ? h.w + tl.hook_off + w + (long long)t * p.in_es : nullptr;
-      T wv[R];
+      // Float32 holds 16 points per thread under a 64-register cap: its transform-index factors are loaded where they are used
+      constexpr bool EARLY_KT = sizeof(T) == 8;
+      T wv[R], kq[EARLY_KT ? R : 1];
 #pragma unroll
-      for (int m = 0; m < R; ++m) wv[m] = wp ? __ldcs(wp + (long long)m * p.in_ms) : T(1);   // independent loads first
+      for (int m = 0; m < R; ++m) wv[m] = wp ? __ldcs(wp + (long long)m * p.in_ms) : T(1);
+      if constexpr (EARLY_KT) {
+#pragma unroll
+        for (int m = 0; m < R; ++m) kq[m] = h.kt ? __ldg(h.kt + (h.idm * (t + m * Tn) + h.ido * tl.o_lo)) : T(1);
+      }
+      unsigned ci0, cio;
+      col_coords(line, (unsigned)h.n0, ci0, cio);
+      const int i0 = (int)ci0;
+      const long long io = h.other_from_col == 1 ? (long long)cio : (h.other_from_col == 2 ? (long long)tl.o_lo : tl.o_hi);
       T fr0 = h.cr, fi0 = h.ci;
       if (h.k0) { const T q = __ldg(h.k0 + i0); fr0 *= q; fi0 *= q; }
+      const T qo = h.ko ? __ldg(h.ko + io) : T(1);
 #pragma unroll
       for (int m = 0; m < R; ++m) {
-        const int it = h.idm * (t + m * Tn) + h.ido * tl.o_lo;
         T fr = fr0, fi = fi0;
-        if (h.kt) { const T q = __ldg(h.kt + it); fr *= q; fi *= q; }
-        if (h.ko) { const T q = __ldg(h.ko + io); fr *= q; fi *= q; }
+        if (h.kt) {
+          const T q = EARLY_KT ? kq[EARLY_KT ? m : 0] : __ldg(h.kt + (h.idm * (t + m * Tn) + h.ido * tl.o_lo));
+          fr *= q; fi *= q;
+        }
+        if (h.ko) { fr *= qo; fi *= qo; }
         if (wp) { fr *= wv[m]; fi *= wv[m]; }
         v[m] = mk<T>(fr, fi) * v[m];
       }
@@ -110,9 +146,11 @@ FFB_D void fs_tile(const FsParams<T>& p, const cx<T>* pin, cx<T>* pout, const Fs
   if constexpr (HOOK && !IS_A) {
     // epilogue: out = dealias( F * (sc * y) + G * acc ), F = (cr + i ci) k0 kt ko w, G = (ar + i ai) a0 at ao
     const typename Pow2Params<T>::Fuse& h = p.hook;
-    const long long line = tl.line0 + w;
-    const int i0 = (int)(line % h.n0);
-    const long long io = h.other_from_col == 1 ? line / h.n0 : (h.other_from_col == 2 ? (long long)tl.o_lo : tl.o_hi);
+    const unsigned line = (unsigned)(tl.line0 + w);
+    unsigned ci0, cio;
+    col_coords(line, (unsigned)h.n0, ci0, cio);
+    const int i0 = (int)ci0;
+    const long long io = h.other_from_col == 1 ? (long long)cio : (h.other_from_col == 2 ? (long long)tl.o_lo : tl.o_hi);
     const bool dead0 = h.dealias && ((h.lo0 > 0 && i0 >= h.lo0 - 1 && i0 < h.hi0) || (h.loo > 0 && io >= h.loo - 1 && io < h.hio));
     const long long hb = tl.hook_off + w + (long long)t * p.out_es;
     cx<T> av[R];
@@ -231,6 +269,22 @@ __global__ void __launch_bounds__(THREADS, MINB) fs_pass_multi_kernel(const __gr
   tl.in_off = tl.o_lo * q0.in_os + tl.o_hi * q0.in_os2 + tl.line0;
   tl.out_off = tl.o_lo * q0.out_os + tl.o_hi * q0.out_os2 + tl.line0;
   tl.hook_off = tl.in_off;
+  // dense factors of the later variants: on their way from DRAM to L2 while variant 0 runs (one request per 128-byte line)
+  {
+    const int w = threadIdx.x & (q0.p.W - 1), t = threadIdx.x >> q0.p.lgW;
+    const T* prev = nullptr;
+#pragma unroll 1
+    for (int v = 1; v < mq.nv; ++v) {
+      const T* wq = mq.q[v].p.hook.w;
+      if (wq && wq != prev && w < tl.ncols) {
+        const T* a = wq + tl.hook_off + w + (long long)t * q0.p.in_es;
+#pragma unroll
+        for (int m = 0; m < PL::R; ++m)
+          if (w == 0 || (reinterpret_cast<uintptr_t>(a + (long long)m * q0.p.in_ms) & 127) < sizeof(T)) prefetch_l2(a + (long long)m * q0.p.in_ms);
+      }
+      prev = wq;
+    }
+  }
   // all but the last variant load with .cg (normal L2 priority: the tile is about to be read again), the last one streams (.cs)
 #pragma unroll 1
   for (int v = 0; v + 1 < mq.nv; ++v) {

@@ -383,6 +383,8 @@ static int pow2_pass(int N, int mode, int dir, const void* in, void* out, long l
   const size_t smem = pow2_smem_bytes<T>(N, p.W, mode);
   const long long gx = (nlines + p.W - 1) / p.W;
   FFB_REQUIRE(gx < (1ll << 31), FFB_EUNSUPPORTED, "too many lines for one launch");
+  const bool cols_mode = mode == C2C_COLS || mode == C2C_COLS_TW || mode == C2C_COLS_LEAN;
+  FFB_REQUIRE(!cols_mode || nlines < (1ll << 31), FFB_EUNSUPPORTED, "too many columns for a strided pass");   // col_coords: 32-bit column index
   static const char* mode_names[6] = {"c2c_rows", "c2c_cols", "r2c_rows", "c2r_rows", "c2c_cols_tw", "c2c_cols"};
   char pname[64];
   snprintf(pname, sizeof(pname), "fft_%s_%s_N%d", mode_names[mode], sizeof(T) == 8 ? "f64" : "f32", N);
@@ -505,7 +507,7 @@ static int fs_pass(const DimTables<T>* tb, int part, long long inner, long long 
   const int Nsub = is_a ? N1 : N2;
   const size_t smem = pow2_smem_bytes<T>(Nsub, q.p.W, C2C_COLS);
   const long long gx = (inner + q.p.W - 1) / q.p.W;
-  FFB_REQUIRE(gx < (1ll << 31) && q.mod <= 65535, FFB_EUNSUPPORTED, "too many lines for one launch");
+  FFB_REQUIRE(inner < (1ll << 31) && q.mod <= 65535, FFB_EUNSUPPORTED, "too many lines for one launch");   // fs_tile: 32-bit column index
   char pname[64];
   snprintf(pname, sizeof(pname), "fft_fs_%s_%s_N%d", is_a ? "a" : "b", sizeof(T) == 8 ? "f64" : "f32", Nsub);
   const double lines = (double)inner * (double)outer;
@@ -558,7 +560,7 @@ static int fs_pass_multi(const DimTables<T>* tb, long long inner, long long oute
   const int W = mq.q[0].p.W;
   const size_t smem = pow2_smem_bytes<T>(N1, W, C2C_COLS);
   const long long gx = (inner + W - 1) / W;
-  FFB_REQUIRE(gx < (1ll << 31) && N2 <= 65535, FFB_EUNSUPPORTED, "too many lines for one launch");
+  FFB_REQUIRE(inner < (1ll << 31) && N2 <= 65535, FFB_EUNSUPPORTED, "too many lines for one launch");
   char pname[64];
   snprintf(pname, sizeof(pname), "fft_fs_am_%s_N%d", sizeof(T) == 8 ? "f64" : "f32", N1);
   ProfScope ps(pname, lines * (1.0 + nv) * N * sizeof(cx<T>) + w_bytes);

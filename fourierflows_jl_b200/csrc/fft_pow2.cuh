@@ -39,12 +39,19 @@ struct DeadCols {
   // transform index is in [tlo, thi) are not stored (the pass that feeds the exchange does not send aliased modes)
   int bylo, byhi, tlo, thi;
 };
+// Column coordinates (i0, other) of line `c`: lines are < 2^31 (host check), so 32-bit arithmetic -- a 64-bit division is a
+// subroutine call in front of every tile's loads -- and no division at all when the pass has a single row of columns (2-D).
+FFB_D void col_coords(unsigned c, unsigned n0, unsigned& i0, unsigned& other) {
+  if (c < n0) { i0 = c; other = 0; }
+  else { other = c / n0; i0 = c - other * n0; }
+}
 FFB_D bool cols_all_dead(const DeadCols& d, long long first, int ncols) {
   if (!d.on || ncols <= 0) return false;
-  const long long last = first + ncols - 1;
-  const long long r0 = first / d.n0, r1 = last / d.n0;
-  if (d.ohi > d.olo && r0 >= d.olo && r1 < d.ohi) return true;
-  if (d.dhi > d.dlo && r0 == r1) { const int a = (int)(first - r0 * d.n0), b = (int)(last - r0 * d.n0); return a >= d.dlo && b < d.dhi; }
+  unsigned a, b, r0, r1;
+  col_coords((unsigned)first, (unsigned)d.n0, a, r0);
+  col_coords((unsigned)first + (unsigned)ncols - 1u, (unsigned)d.n0, b, r1);
+  if (d.ohi > d.olo && (int)r0 >= d.olo && (int)r1 < d.ohi) return true;
+  if (d.dhi > d.dlo && r0 == r1) return (int)a >= d.dlo && (int)b < d.dhi;
   return false;
 }
 
@@ -448,8 +455,10 @@ FFB_D void fft_pow2_tile(const Pow2Params<T>& p, const unsigned bx, const unsign
     }
     after_load();
     if (p.pro.on && active) {
-      const int i0 = (int)(line % p.pro.n0);
-      const long long io = p.pro.other_from_col == 1 ? line / p.pro.n0 : (p.pro.other_from_col == 2 ? (long long)o_lo : o_hi);
+      unsigned ci0, cio;
+      col_coords((unsigned)line, (unsigned)p.pro.n0, ci0, cio);
+      const int i0 = (int)ci0;
+      const long long io = p.pro.other_from_col == 1 ? (long long)cio : (p.pro.other_from_col == 2 ? (long long)o_lo : o_hi);
       const long long base = (in - reinterpret_cast<const cx<T>*>(pin));
       // the dense factor is loaded in batches (independent loads first, uses after) so its latency is paid once per batch
       constexpr int PB = R < 8 ? R : 8;
@@ -579,8 +588,10 @@ FFB_D void fft_pow2_tile(const Pow2Params<T>& p, const unsigned bx, const unsign
       const T sc = p.scale;
       auto off = [&](int i) { return (long long)(i & p.out_seg_mask) * p.out_es + (long long)(i >> p.out_seg_shift) * p.out_seg_stride; };
       if (p.epi.on) {
-        const int i0 = (int)(line % p.epi.n0);
-        const long long io = p.epi.other_from_col == 1 ? line / p.epi.n0 : (p.epi.other_from_col == 2 ? (long long)o_lo : o_hi);
+        unsigned ci0, cio;
+        col_coords((unsigned)line, (unsigned)p.epi.n0, ci0, cio);
+        const int i0 = (int)ci0;
+        const long long io = p.epi.other_from_col == 1 ? (long long)cio : (p.epi.other_from_col == 2 ? (long long)o_lo : o_hi);
         const long long base = (out - reinterpret_cast<cx<T>*>(pout));
         const bool dead0 = p.epi.dealias && ((p.epi.lo0 > 0 && i0 >= p.epi.lo0 - 1 && i0 < p.epi.hi0) || (p.epi.loo > 0 && io >= p.epi.loo - 1 && io < p.epi.hio));
         constexpr int EB = R < 4 ? R : 4;

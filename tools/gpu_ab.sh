@@ -4,7 +4,7 @@
 OUT=gpurun_out
 mkdir -p $OUT
 ALT=$PWD/fourierflows_jl_b200/lib_ab/libfourierflows_b200.so
-echo "== pytest -m gpu"; timeout 600 python -m pytest tests -q -m gpu -x 2>&1 | tail -6 | tee $OUT/ab_pytest_gpu.log
+echo "== pytest -m gpu (${AB_TESTS:-all})"; timeout 600 python -m pytest ${AB_TESTS:-tests} -q -m gpu -x 2>&1 | tail -6 | tee $OUT/ab_pytest_gpu.log
 line() { python - "$1" <<'PY'
 import json, sys
 try:
@@ -18,10 +18,10 @@ except Exception as e:
 PY
 }
 B="python bench.py --no-cpu-baseline --no-weak-ref --steps 20 --warmup 3"
-echo "== bench: in-tree, multi-A on";   timeout 200 $B > $OUT/ab_main_multi1.json 2> $OUT/ab_main_multi1.err; line $OUT/ab_main_multi1.json
-echo "== bench: in-tree, multi-A off";  FFB_MULTI_A=0 timeout 200 $B > $OUT/ab_main_multi0.json 2> $OUT/ab_main_multi0.err; line $OUT/ab_main_multi0.json
+for rep in a b; do
+echo "== bench: in-tree build ($rep)"; timeout 200 $B > $OUT/ab_main_$rep.json 2> $OUT/ab_main_$rep.err; line $OUT/ab_main_$rep.json
 if [ -f "$ALT" ]; then
-echo "== bench: two-phase rows build, multi-A on"; FFB_LIB_PATH=$ALT timeout 200 $B > $OUT/ab_alt_multi1.json 2> $OUT/ab_alt_multi1.err; line $OUT/ab_alt_multi1.json
+echo "== bench: alternative build fourierflows_jl_b200/lib_ab ($rep)"; FFB_LIB_PATH=$ALT timeout 200 $B > $OUT/ab_alt_$rep.json 2> $OUT/ab_alt_$rep.err; line $OUT/ab_alt_$rep.json
 fi
-echo "== bench: in-tree, multi-A on (again)"; timeout 200 $B > $OUT/ab_main_multi1b.json 2> $OUT/ab_main_multi1b.err; line $OUT/ab_main_multi1b.json
-echo "== bench c2"; timeout 200 python bench.py --workload c2 > $OUT/r02_bench_c2_n1.json 2> $OUT/r02_bench_c2_n1.err; cut -c1-600 $OUT/r02_bench_c2_n1.json
+done
+if [ -n "$AB_EXTRA" ]; then echo "== $AB_EXTRA"; bash -c "$AB_EXTRA"; fi
