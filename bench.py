@@ -69,6 +69,7 @@ def stage_bytes(stepper, S, R, cw):
     return 3 * S + R + f
 
 
+PIPELINE_MAX_BYTES = 3 << 29   # e2e through the host-buffer pipeline when the state is at most 1.5 GB per GPU (6 pinned host buffers)
 NCALC = {"ETDRK4": 4, "RK4": 4, "LSRK54": 5, "AB3": 1, "ForwardEuler": 1}
 
 
@@ -615,7 +616,35 @@ def run_gpu(args):
             L.call("ffb_h2d", prob.sol.ptr, hp, S)      # this step's input state (this rank's slab) from pinned host memory
             prob.stepforward(1)                          # public call: ffb_step
             L.call("ffb_d2h", hp, prob.sol.ptr, S)       # result back to the host (blocking)
-        e2e_ms = timed(e2e_step, max(1, min(args.steps, 5)))
+        e2e_serial_ms = timed(e2e_step, max(1, min(args.steps, 5)))
+        e2e_ms, e2e_mode = e2e_serial_ms, {"mode": "blocking: ffb_h2d, ffb_step, ffb_d2h one after the other"}
+        if S <= PIPELINE_MAX_BYTES and "AB3" not in wl.stepper:
+            # the same work through the host-buffer pipeline (ffb_pipeline_*): every step is an independent host state -- uploaded from
+            # pinned memory, stepped once, downloaded -- and the copies of neighbouring steps run beside the step on two copy streams
+            depth, nsub = 3, max(6, min(args.steps, 12))
+            host_state = np.frombuffer((C.c_char * S).from_address(hp.value), dtype=np.uint8)
+            ins = [ff.PinnedBuffer((S,), np.uint8) for _ in range(depth)]
+            outs = [ff.PinnedBuffer((S,), np.uint8) for _ in range(depth)]
+            for b in ins:
+                b.array[:] = host_state
+            pipe = prob.pipeline(depth)
+
+            def e2e_pipelined():
+                for i in range(nsub):
+                    pipe.submit(ins[i % depth], outs[i % depth], 1)
+                pipe.wait_all()
+            e2e_pipelined()                                                                       # warm-up, and the check below
+            e2e_step()                                                                            # blocking form on the same input
+            same = bool(np.array_equal(outs[0].array, host_state) and np.array_equal(outs[depth - 1].array, host_state))
+            e2e_ms = timed(e2e_pipelined, 1) / nsub
+            e2e_mode = {"mode": f"pipelined (ffb_pipeline_*, depth {depth}, {nsub} submissions timed): every step is an independent host state, uploaded from "
+                                "pinned memory, stepped once and downloaded; the copies of neighbouring steps overlap the step on two copy streams",
+                        "matches_blocking_form_bitwise": same,
+                        "blocking": {"ms_per_step": e2e_serial_ms, "value": wl.replicas * 1e3 / e2e_serial_ms * wl.points() / 1e9}}
+            pipe.close()
+            del host_state
+            for b in ins + outs:
+                b.close()
         L.call("ffb_host_free_pinned", hp)
         dev_bytes = prob.device_bytes()
 
@@ -643,7 +672,7 @@ def run_gpu(args):
                 "alltoall_gbs_per_gpu_rfft": (nvlink_bytes / nfft) / fft_ms["rfft"] / 1e6 if nvlink_bytes else None},
         "roofline": roofline, "kernels": kernels,
         "e2e": {"value": wl.replicas * 1e3 / e2e_ms * wl.points() / 1e9, "unit": "Gpt*steps/s", "steps_per_s": wl.replicas * 1e3 / e2e_ms,
-                "h2d_bytes_per_step": S * world, "d2h_bytes_per_step": S * world, "ms_per_step": e2e_ms},
+                "h2d_bytes_per_step": S * world, "d2h_bytes_per_step": S * world, "ms_per_step": e2e_ms, **e2e_mode},
         "gpu_launches": launches, "clocks": clocks,
     }
     if weak_ref is not None:

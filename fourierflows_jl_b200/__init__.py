@@ -19,7 +19,7 @@ from .utils import axpby, jacobian, jacobianh, mul, mul_real, parsevalsum, parse
 from .output import AsyncSnapshot, Output, gather_to_rank0, saveoutput
 from . import diffusion as Diffusion
 from .equations import Burgers3D, TwoDNavierStokes
-from .cproblem import CProblem
+from .cproblem import CProblem, HostPipeline, PinnedBuffer
 from .dist import (Dist, DistPlan, exchange_bytes_per_rank, gather_spectral_2d, local_alias_range, local_kx_alias_2d, physical_slab,
                    physical_slab_2d, slab_range, spectral_slab, spectral_slab_2d)
 

@@ -143,6 +143,10 @@ SIGNATURES = {
     "ffb_problem_get_physical": [_vp, _vp],
     "ffb_step": [_vp, _i64],
     "ffb_step_until": [_vp, _d],
+    "ffb_pipeline_create": [_P(_vp), _vp, _i],
+    "ffb_pipeline_destroy": [_vp],
+    "ffb_pipeline_submit": [_vp, _vp, _vp, _i64, _P(_i)],
+    "ffb_pipeline_wait": [_vp, _i],
 }
 
 _lib = None

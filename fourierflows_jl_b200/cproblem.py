@@ -104,12 +104,80 @@ class CProblem:
     def step_until(self, stop_time):
         L.call("ffb_step_until", self._h, float(stop_time))
 
+    def pipeline(self, depth=3):
+        """host-buffer pipeline of this problem (`ffb_pipeline_*`): see `HostPipeline`"""
+        return HostPipeline(self, depth)
+
     def close(self):
         if getattr(self, "_h", None):
             L.load().ffb_problem_destroy(self._h)
             self._h = None
             if getattr(self, "sol", None) is not None:
                 self.sol.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class PinnedBuffer:
+    """Page-locked host array (`ffb_host_alloc_pinned`) viewed as a Fortran-ordered NumPy array."""
+
+    def __init__(self, shape, dtype):
+        self.shape, self.dtype = tuple(shape), np.dtype(dtype)
+        self.nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        p = C.c_void_p()
+        L.call("ffb_host_alloc_pinned", C.byref(p), self.nbytes)
+        self.ptr = p.value
+        self.array = np.frombuffer((C.c_char * self.nbytes).from_address(self.ptr), dtype=self.dtype).reshape(self.shape, order="F")
+
+    def close(self):
+        if getattr(self, "ptr", None):
+            self.array = None
+            L.load().ffb_host_free_pinned(C.c_void_p(self.ptr))
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class HostPipeline:
+    """Independent spectral states in pinned host memory, stepped on the GPU with the copies of neighbouring submissions
+    overlapping the steps of the current one (no reference counterpart; the blocking form is `sol .= ...; stepforward!; Array(sol)`).
+
+        pipe = prob.pipeline(depth=3)
+        t = pipe.submit(inp, out, nsteps=1)     # PinnedBuffer in / out; returns at once unless `depth` submissions are in flight
+        pipe.wait(t)                            # out.array now holds the stepped state
+    """
+
+    def __init__(self, prob: CProblem, depth=3):
+        h = C.c_void_p()
+        L.call("ffb_pipeline_create", C.byref(h), prob._h, int(depth))
+        self._h, self.prob, self.depth = h, prob, int(depth)
+
+    def submit(self, inp: PinnedBuffer, out: PinnedBuffer, nsteps=1) -> int:
+        if inp.nbytes != self.prob.sol.nbytes or out.nbytes != self.prob.sol.nbytes:
+            raise ValueError("host buffers must have the size of prob.sol")
+        t = C.c_int(-1)
+        L.call("ffb_pipeline_submit", self._h, C.c_void_p(inp.ptr), C.c_void_p(out.ptr), int(nsteps), C.byref(t))
+        return t.value
+
+    def wait(self, ticket: int) -> None:
+        L.call("ffb_pipeline_wait", self._h, int(ticket))
+
+    def wait_all(self) -> None:
+        for t in range(self.depth):
+            self.wait(t)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            L.load().ffb_pipeline_destroy(self._h)
+            self._h = None
 
     def __del__(self):
         try:

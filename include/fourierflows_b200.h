@@ -321,6 +321,19 @@ int ffb_step(ffb_problem* prob, int64_t nsteps);
 /* `step_until!(prob, stop_time)` src/timesteppers.jl:734-760 (bug-compatible final step, FFB_ESTEPPER for ETDRK4) */
 int ffb_step_until(ffb_problem* prob, double stop_time);
 
+/* Host-buffer pipeline (no reference counterpart: with CUDA.jl the user writes `prob.sol .= device_array(dev)(host)`,
+ * `stepforward!`, `Array(prob.sol)` -- three blocking calls, src/utils.jl:330, src/timesteppers.jl:14, src/output.jl:79 -- and the GPU
+ * idles during both copies).  Each submission is an independent spectral state in pinned host memory (an ensemble member, a request):
+ * it is uploaded on a copy-in stream, moved into `sol`, stepped `nsteps` times on the library stream and downloaded into `host_out`
+ * on a copy-out stream, so that the copies of neighbouring submissions overlap the steps of this one.  `depth` = submissions in
+ * flight (device staging: 2 x depth spectral arrays).  ffb_pipeline_submit blocks only when the ring is full; `host_out` is complete
+ * after ffb_pipeline_wait(ticket).  Results equal h2d + ffb_step + d2h bit for bit.  FFB_EUNSUPPORTED for AB3 (history). */
+typedef struct ffb_pipeline ffb_pipeline;
+int ffb_pipeline_create(ffb_pipeline** pipe, ffb_problem* prob, int depth);
+int ffb_pipeline_destroy(ffb_pipeline* pipe);
+int ffb_pipeline_submit(ffb_pipeline* pipe, const void* host_in, void* host_out, int64_t nsteps, int* ticket);
+int ffb_pipeline_wait(ffb_pipeline* pipe, int ticket);
+
 #ifdef __cplusplus
 }
 #endif

@@ -119,3 +119,55 @@ def test_async_snapshots_do_not_see_later_steps(ff, tmp_path):
     out.close()
     f = np.load(str(tmp_path / "run_snapshot_5.npz"))
     assert np.array_equal(f["snapshots/sol/5"], held) and float(f["snapshots/t/5"]) == float(5 * 1e-3) or np.isclose(float(f["snapshots/t/5"]), 5e-3)
+
+
+@pytest.mark.parametrize("kw", [dict(n=(256, 256), stepper="ETDRK4", calcN="vorticity2d", nu=1e-3, T=np.float64, fused=1),
+                                dict(n=(128, 64), stepper="FilteredRK4", calcN="vorticity2d", nu=1e-3, T=np.float32, fused=0),
+                                dict(n=(32, 32, 32), stepper="LSRK54", calcN="burgers3d", nu=1e-2, T=np.float32, fused=1)],
+                         ids=["etdrk4-2d-f64", "filtered-rk4-2d-f32", "lsrk54-3d-f32"])
+def test_host_pipeline_equals_blocking_form(ff, kw):
+    """ffb_pipeline_*: independent host states (pinned), uploaded / stepped / downloaded with the copies of neighbouring submissions
+    overlapping the steps, must equal h2d + ffb_step + d2h bit for bit -- more submissions than slots (the ring wraps), nsteps = 2,
+    outputs read only after their ticket.  AB3 keeps history across steps: FFB_EUNSUPPORTED."""
+    kw = dict(kw)
+    n = kw.pop("n")
+    prob = ff.CProblem(n, 2 * np.pi, dt=1e-3, **kw)
+    cT = prob.sol.dtype
+    rng = np.random.default_rng(5)
+    nsub, depth, nsteps = 5, 2, 2
+    states = []
+    for _ in range(nsub):
+        prob.set_physical(np.asfortranarray(rng.standard_normal(prob.physical_shape).astype(prob.T)))
+        states.append(prob.sol.to_numpy().copy())
+    # blocking form
+    expect = []
+    for s in states:
+        prob.sol.copy_from_host(s)
+        prob.stepforward(nsteps)
+        expect.append(prob.sol.to_numpy().copy())
+    ins = [ff.PinnedBuffer(prob.spectral_shape, cT) for _ in range(nsub)]
+    outs = [ff.PinnedBuffer(prob.spectral_shape, cT) for _ in range(nsub)]
+    for b, s in zip(ins, states):
+        b.array[...] = s
+    pipe = prob.pipeline(depth)
+    tickets = [pipe.submit(ins[i], outs[i], nsteps) for i in range(nsub)]
+    assert tickets == [i % depth for i in range(nsub)]
+    pipe.wait_all()
+    for i in range(nsub):
+        assert np.isfinite(outs[i].array).all()
+        assert np.array_equal(outs[i].array, expect[i]), f"submission {i}"
+    # a second round on the same pipeline, nsteps = 0: the state comes back unchanged
+    t = pipe.submit(ins[0], outs[1], 0)
+    pipe.wait(t)
+    assert np.array_equal(outs[1].array, states[0])
+    with pytest.raises(ValueError):
+        pipe.submit(ff.PinnedBuffer((4,), cT), outs[0], 1)
+    pipe.close()
+    for b in ins + outs:
+        b.close()
+    prob.close()
+    ab3 = ff.CProblem((64, 64), 2 * np.pi, stepper="AB3", dt=1e-3, calcN="vorticity2d", nu=1e-3)
+    with pytest.raises(ff.FFBError) as ei:
+        ab3.pipeline(2)
+    assert ei.value.code == ff._lib.FFB_EUNSUPPORTED
+    ab3.close()
