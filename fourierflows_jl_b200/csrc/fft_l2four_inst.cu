@@ -66,6 +66,8 @@ static int l2_dispatch(int op, int N1, int N2, int dir, int hook, const L2FourPa
 template <int DIR, bool IS_A, bool HOOK, int N>
 static int fs_one(const FsLaunch<real_t>& q, dim3 grid, size_t smem, cudaStream_t st) {
   using PL = typename fs_plan_for<real_t, N>::type;
+  // (measured: squeezing the hook-free Float64 sub-passes to 64 registers for 4 CTAs = 32 warps per SM changes nothing, 14.93 vs
+  // 14.84 ms per C3 step -- they are no longer latency-bound)
   auto kern = fs_pass_kernel<real_t, DIR, IS_A, HOOK, PL, kFsThreads, kMinB>;
   static size_t configured = 0;
   int rc = configure(kern, smem, configured);

@@ -529,6 +529,15 @@ ldiv!(out::B200Array, p::B200Plan, ah::B200Array, f::FFBFuse) =
   (check(ccall((:ffb_fft_inverse_ex, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{FFBFuse}), p.handle, ah.ptr, out.ptr, Ref(f))); out)
 mul!(out::B200Array, p::B200Plan, a::B200Array, f::FFBFuse) =
   (check(ccall((:ffb_fft_forward_ex, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{FFBFuse}), p.handle, a.ptr, out.ptr, Ref(f))); out)
+"`ldiv!(outs, plan, ah, fuses)`: outs[v] = irfft(factor_v .* ah) [.* mul_v] for every v, in order; `ah` (and a dense factor the variants share)
+is read once by the first four-step sub-pass (zeta, u, v of a vorticity calcN! from one `sol`)"
+function ldiv!(outs::Vector{<:B200Array}, p::B200Plan, ah::B200Array, fs::Vector{FFBFuse})
+  length(outs) == length(fs) || throw(ArgumentError("one FFBFuse per output"))
+  ptrs = Ptr{Cvoid}[o.ptr for o in outs]
+  GC.@preserve outs check(ccall((:ffb_fft_inverse_multi, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ptr{Ptr{Cvoid}}, Ptr{FFBFuse}),
+                                p.handle, ah.ptr, length(outs), ptrs, fs))
+  return outs
+end
 
 # ---------------------------------------------------------------- `jacobianh` (src/utils.jl:190-197) and the asynchronous output path
 function FourierFlows.jacobianh(a::B200Array{T,2}, b::B200Array{T,2}, g::TwoDGrid) where T<:AbstractFloat
@@ -586,6 +595,31 @@ function B200Problem(cfg::FFBProblemConfig)
 end
 stepforward!(p::B200Problem, nsteps::Integer=1) = check(ccall((:ffb_step, lib), Cint, (Ptr{Cvoid}, Int64), p.handle, nsteps))   # src/timesteppers.jl:14-20
 FourierFlows.step_until!(p::B200Problem, stop_time) = check(ccall((:ffb_step_until, lib), Cint, (Ptr{Cvoid}, Cdouble), p.handle, stop_time))  # :734-760
+
+# Host-buffer pipeline: independent spectral states in pinned host memory (`pinned(T, dims)`), uploaded / stepped / downloaded with the
+# copies of neighbouring submissions beside the steps -- instead of `sol .= A(h); stepforward!(prob); Array(sol)`, which idles the GPU
+# during both copies.  `t = submit!(pipe, hin, hout, nsteps)`; `wait(pipe, t)`: `hout` holds the stepped state.
+function pinned(::Type{T}, dims::Dims) where T
+  p = Ref{Ptr{Cvoid}}(C_NULL)
+  check(ccall((:ffb_host_alloc_pinned, lib), Cint, (Ptr{Ptr{Cvoid}}, Csize_t), p, prod(dims) * sizeof(T)))
+  a = unsafe_wrap(Array, Ptr{T}(p[]), dims)
+  finalizer(x -> ccall((:ffb_host_free_pinned, lib), Cint, (Ptr{Cvoid},), pointer(x)), a)
+  return a
+end
+mutable struct HostPipeline; handle :: Ptr{Cvoid}; depth :: Int; end
+function HostPipeline(prob::B200Problem, depth::Integer=3)
+  h = Ref{Ptr{Cvoid}}(C_NULL)
+  check(ccall((:ffb_pipeline_create, lib), Cint, (Ptr{Ptr{Cvoid}}, Ptr{Cvoid}, Cint), h, prob.handle, depth))
+  q = HostPipeline(h[], depth)
+  finalizer(x -> ccall((:ffb_pipeline_destroy, lib), Cint, (Ptr{Cvoid},), x.handle), q)
+  return q
+end
+function submit!(q::HostPipeline, hin::Array, hout::Array, nsteps::Integer=1)
+  t = Ref{Cint}(-1)
+  check(ccall((:ffb_pipeline_submit, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cint}), q.handle, hin, hout, nsteps, t))
+  return t[]
+end
+Base.wait(q::HostPipeline, ticket::Integer) = check(ccall((:ffb_pipeline_wait, lib), Cint, (Ptr{Cvoid}, Cint), q.handle, ticket))
 
 # ---------------------------------------------------------------- multi-GPU: one Julia process per GPU (MPI.jl moves the id and the IPC handles)
 # comm = MPI.COMM_WORLD; id = Vector{UInt8}(undef, 128); rank == 0 && ffb_dist_unique_id(id); MPI.Bcast!(id, 0, comm)
