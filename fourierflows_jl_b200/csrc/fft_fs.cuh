@@ -153,23 +153,47 @@ FFB_D void fs_tile(const FsParams<T>& p, const cx<T>* pin, cx<T>* pout, const Fs
     const long long io = h.other_from_col == 1 ? (long long)cio : (h.other_from_col == 2 ? (long long)tl.o_lo : tl.o_hi);
     const bool dead0 = h.dealias && ((h.lo0 > 0 && i0 >= h.lo0 - 1 && i0 < h.hi0) || (h.loo > 0 && io >= h.loo - 1 && io < h.hio));
     const long long hb = tl.hook_off + w + (long long)t * p.out_es;
-    cx<T> av[R];
-    bool dead[R];
+    // loop-invariant operands first (factor order as in fuse_factor: scalar, k0[i0], kt[it], ko[io], w)
+    T fr0 = h.cr, fi0 = h.ci, gr0 = h.ar, gi0 = h.ai;
+    if (h.k0) { const T q = __ldg(h.k0 + i0); fr0 *= q; fi0 *= q; }
+    if (h.acc && h.a0) { const T q = __ldg(h.a0 + i0); gr0 *= q; gi0 *= q; }
+    const T qo = h.ko ? __ldg(h.ko + io) : T(1);
+    const T go = (h.acc && h.ao) ? __ldg(h.ao + io) : T(1);
+    // Two halves: R accumulated values beside the R data points do not fit the register budget (the one-batch form spilled 40-72
+    // bytes per thread); the accumulated tile is already on its way to L2 (prefetch at tile start).
+    constexpr int H = R / 2;
 #pragma unroll
-    for (int m = 0; m < R; ++m) {   // independent loads of the accumulated array first
-      const int it = h.idm * (t + m * Tn) + h.ido * tl.o_lo;
-      dead[m] = dead0 || (h.dealias && h.lot > 0 && it >= h.lot - 1 && it < h.hit);
-      av[m] = (h.acc && !dead[m]) ? ldc(h.acc + hb + (long long)m * p.out_ms) : mk<T>(0, 0);
-    }
+    for (int half = 0; half < 2; ++half) {
+      cx<T> av[H];
+      bool dead[H];
 #pragma unroll
-    for (int m = 0; m < R; ++m) {
-      const int it = h.idm * (t + m * Tn) + h.ido * tl.o_lo;
-      cx<T> r = mk<T>(0, 0);
-      if (!dead[m]) {
-        r = fuse_factor<T>(h.cr, h.ci, h.k0, h.kt, h.ko, h.w, i0, it, io, hb + (long long)m * p.out_ms) * (sc * v[m]);
-        if (h.acc) r = r + fuse_factor<T>(h.ar, h.ai, h.a0, h.at, h.ao, (const T*)nullptr, i0, it, io, 0) * av[m];
+      for (int j = 0; j < H; ++j) {   // independent loads of the accumulated array first
+        const int m = half * H + j;
+        const int it = h.idm * (t + m * Tn) + h.ido * tl.o_lo;
+        dead[j] = dead0 || (h.dealias && h.lot > 0 && it >= h.lot - 1 && it < h.hit);
+        av[j] = (h.acc && !dead[j]) ? ldc(h.acc + hb + (long long)m * p.out_ms) : mk<T>(0, 0);
       }
-      stc(out + (long long)m * p.out_ms, r);
+#pragma unroll
+      for (int j = 0; j < H; ++j) {
+        const int m = half * H + j;
+        const int it = h.idm * (t + m * Tn) + h.ido * tl.o_lo;
+        cx<T> r = mk<T>(0, 0);
+        if (!dead[j]) {
+          T fr = fr0, fi = fi0;
+          if (h.kt) { const T q = __ldg(h.kt + it); fr *= q; fi *= q; }
+          if (h.ko) { fr *= qo; fi *= qo; }
+          if (h.w) { const T q = __ldcs(h.w + hb + (long long)m * p.out_ms); fr *= q; fi *= q; }
+          r = mk<T>(fr, fi) * (sc * v[m]);
+          if (h.acc) {
+            T gr = gr0, gi = gi0;
+            if (h.at) { const T q = __ldg(h.at + it); gr *= q; gi *= q; }
+            if (h.ao) { gr *= go; gi *= go; }
+            r = r + mk<T>(gr, gi) * av[j];
+          }
+        }
+        // dealias = 2: the alias box is don't-care, nothing is stored there
+        if (!(dead[j] && h.dealias == 2)) stc(out + (long long)m * p.out_ms, r);
+      }
     }
   } else {
     if (sc != T(1)) {
