@@ -75,3 +75,24 @@ def test_product_does_not_import_oracle():
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert not re.search(r"^\s*(import|from)\s+oracle\b", text, flags=re.M), f"{f} imports the oracle"
                 assert "scipy" not in text or f == "__init__.py", f"{f} must not lean on a CPU FFT"
+
+
+def test_new_entry_points_validate_arguments_without_a_device(lib):
+    """ffb_fft_inverse_multi / ffb_pipeline_* reject NULL handles with FFB_EINVAL before they touch the device (host-side contract,
+    checked here on the CPU; the compute behaviour is covered by the -m gpu tests)."""
+    import fourierflows_jl_b200 as ff
+    L = ff._lib
+    L.load()
+    null = C.c_void_p()
+    outs = (C.c_void_p * 1)(None)
+    fuse = (L.ffb_fuse * 1)()
+    assert lib.ffb_fft_inverse_multi(None, None, 1, outs, fuse) == L.FFB_EINVAL
+    assert lib.ffb_pipeline_create(C.byref(null), None, 2) == L.FFB_EINVAL and not null.value
+    t = C.c_int(-1)
+    assert lib.ffb_pipeline_submit(None, None, None, 1, C.byref(t)) == L.FFB_EINVAL
+    assert lib.ffb_pipeline_wait(None, 0) == L.FFB_EINVAL
+    assert lib.ffb_pipeline_destroy(None) == L.FFB_OK
+    # pinned host memory needs the CUDA runtime: without a device the allocation fails loudly, it does not fall back to malloc
+    if not ff.have_device():
+        with pytest.raises(ff.FFBError):
+            ff.PinnedBuffer((16,), "float64")
