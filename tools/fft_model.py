@@ -111,6 +111,35 @@ def bank_conflicts(N, R, radices, wordbytes, pad_every, pad_words=1, W=1):
     return res, worst
 
 
+def c3_step_traffic(n, aliased_fraction=1 / 3, es=8):
+    """DRAM bytes one ETDRK4 step of the fused 2-D vorticity problem (config C3) moves in THIS implementation, kernel class by kernel
+    class, for an n x n grid whose y dimension is four-step (n >= 4096).  S = spectral array, P = physical array, R = dense real
+    spectral-shaped array; f / g = live fraction of the kx columns / ky rows (alias ranges: src/domains.jl:408-427).
+      inverse (zeta, u, v from one sol, ffb_fft_inverse_multi): shared sub-pass A reads S + R (invKrsq once) and writes 3 S;
+        3 sub-passes B: 2 S each; 3 c2r row passes: S -> P, two of them also read the zeta field.
+      forward 1 (dealias = 2, box don't-care): r2c P -> f S; sub-pass A f S -> f S; sub-pass B f S -> f g S.
+      forward 2 (dealias = 1): r2c P -> f S; sub-pass A f S -> f S; sub-pass B reads f S + f g S (accumulated), writes S (zeros included).
+      stages (stages.cu, Float64 dense ETD coefficients): 2 x (3 S + 2 R) + (4 S + 2 R) + (6 S + 4 R)."""
+    nkr = n // 2 + 1
+    S, P, R = nkr * n * 2 * es, n * n * es, nkr * n * es
+    iL = int(np.floor((1 - aliased_fraction) / 2 * n)) + 1
+    iR = int(np.ceil((1 + aliased_fraction) / 2 * n))
+    f = 1 - (nkr - iL + 1) / nkr if aliased_fraction > 0 else 1.0
+    g = 1 - (iR - iL + 1) / n if aliased_fraction > 0 else 1.0
+    per_calcN = {
+        "fs_am (shared inverse sub-pass A)": S + R + 3 * S,
+        "fs_b inverse": 3 * 2 * S,
+        "c2r rows": 3 * (S + P) + 2 * P,
+        "r2c rows": 2 * (P + f * S),
+        "fs_a forward": 2 * 2 * f * S,
+        "fs_b forward": (f * S + f * g * S) + (f * S + f * g * S + S),
+    }
+    out = {k: 4 * v for k, v in per_calcN.items()}
+    out["stages"] = 2 * (3 * S + 2 * R) + (4 * S + 2 * R) + (6 * S + 4 * R)
+    out["total"] = sum(out.values())
+    return out
+
+
 def check():
     rng = np.random.default_rng(0)
     for N, R, rad in [(64, 8, [8, 8]), (128, 16, [16, 8]), (256, 16, [16, 16]), (512, 8, [8, 8, 8]), (512, 16, [16, 16, 2]),
