@@ -75,6 +75,7 @@ NCALC = {"ETDRK4": 4, "RK4": 4, "LSRK54": 5, "AB3": 1, "ForwardEuler": 1}
 
 # ------------------------------------------------------------------------------------------------ workloads
 class Workload:
+    l2 = "no flush between timed steps: every array a step touches is far larger than the 126 MB L2"
     replicas = 1
     decomposed = False
     scaling = "strong"
@@ -85,7 +86,7 @@ class Workload:
 
     def config(self):
         """identical in both arms (the driver compares them)"""
-        return {"workload": self.name, "grid": list(self.shape), "stepper": self.stepper, "precision": self.dtype}
+        return {"workload": self.name, "grid": list(self.shape), "stepper": self.stepper, "precision": self.dtype, "l2": self.l2}
 
 
 class Vorticity2D(Workload):
@@ -199,6 +200,7 @@ class Burgers3D(Workload):
 class DerivativeRoundTrip(Workload):
     """C2 of SURVEY 8d: TwoDGrid 4096^2 Float64: uh = rfft(u); ux = irfft(i kr uh); uy = irfft(i l uh) (one "step")."""
     dtype, T, key, stepper, kind = "f64", np.float64, "c2", "none (rfft + 2 x (ik, irfft))", "transform"
+    l2 = "no flush between timed round trips: each of the five arrays a round trip streams (134 MB at 4096^2) is larger than the 126 MB L2"
 
     def __init__(self, n, world):
         self.shape, self.world, self.replicas = (n, n), 1, world

@@ -65,7 +65,7 @@ def test_both_arms_describe_the_same_config(bench):
         workload, n, n3, nz_per_gpu = "auto", 8192, 2048, 256
     for world in (1, 2, 8):
         a, b = bench.make_workload(A(), world), bench.make_workload(A(), world)
-        assert a.config() == b.config() and set(a.config()) == {"workload", "grid", "stepper", "precision"}
+        assert a.config() == b.config() and set(a.config()) == {"workload", "grid", "stepper", "precision", "l2"}
     A.workload = "c4"
     w = bench.make_workload(A(), 4)
     assert tuple(w.shape) == (1024, 1024, 1024) and w.stepper == "FilteredRK4" and w.scaling == "strong" and np.dtype(w.T) == np.float64
