@@ -267,7 +267,7 @@ static int env_int(const char* name, int dflt) {
   return e ? atoi(e) : dflt;
 }
 
-// Lines-per-CTA choice (measured: tools/sweep_w.py, tools/sweep2.py, profiles/r01_sweep_*.log).  Throughput is set by how
+// Lines-per-CTA choice (measured: tools/sweep_w.py, profiles/r01_fft_sweep_v*.log).  Throughput is set by how
 // many independent CTAs an SM can overlap, so CTAs are kept small.  ROWS: one line per CTA (>= 32 threads).
 // COLS: about 256 threads with W adjacent columns clamped to [64 B, 256 B] wide rows (Float64 4..16, Float32 16..32
 // columns, 8 only when 16 do not fit -- N = 2048; the twiddled four-step sub-pass likes 32).
@@ -351,11 +351,11 @@ static int pow2_pass(int N, int mode, int dir, const void* in, void* out, long l
     // distance = one full wave of resident CTAs (tuning override: FFB_PF_AHEAD, 0 disables)
     static int pf_env = -2;
     if (pf_env == -2) { const char* e = getenv("FFB_PF_AHEAD"); pf_env = e ? atoi(e) : -1; }
-    // measured (tools/sweep3.py): +10 % for the Float64 r2c pass of 4096-point lines at one wave ahead, neutral or negative elsewhere
+    // measured (round-1 sweep): +10 % for the Float64 r2c pass of 4096-point lines at one wave ahead, neutral or negative elsewhere
     p.pf_ahead = pf_env >= 0 ? pf_env : ((mode == R2C_ROWS && N * sizeof(cx<T>) >= 32768) ? num_sms() : 0);
   }
   if (mode == C2C_COLS_LEAN) {
-    // measured (tools/stream_sweep.py): +5 % when the tile fills the SM (one CTA per SM), -20 % when several CTAs share an SM
+    // measured (tools/experiments/stream_sweep.py): +5 % when the tile fills the SM (one CTA per SM), -20 % when several CTAs share an SM
     static int pfc = -2;
     if (pfc == -2) { const char* e = getenv("FFB_PF_COLS"); pfc = e ? atoi(e) : -1; }
     p.pf_ahead = pfc >= 0 ? pfc : -1;   // resolved below once the tile shape is known
