@@ -15,7 +15,7 @@ from .domains import (OneDGrid, Plan, ThreeDGrid, TwoDGrid, dealias, getaliasedw
 from .problem import Clock, EmptyParams, EmptyVars, Equation, Problem
 from .timesteppers import (STEPPERS, TimeStepper, getetdcoeffs_and_expLs, isexplicit, step_until, stepforward)
 from .diagnostics import Diagnostic, increment
-from .utils import axpby, jacobian, jacobianh, mul, mul_real, parsevalsum, parsevalsum2, spectral_mul
+from .utils import axpby, fft, ifft, irfft, jacobian, jacobianh, mul, mul_real, parsevalsum, parsevalsum2, rfft, spectral_mul
 from .output import AsyncSnapshot, Output, gather_to_rank0, saveoutput
 from . import diffusion as Diffusion
 from .equations import Burgers3D, TwoDNavierStokes

@@ -142,6 +142,11 @@ ldiv!(out::B200Array, p::B200Plan, ah::B200Array) =                             
 \(p::B200Plan{T,:r2c}, ah::B200Array{Complex{T}}) where T = ldiv!(B200Array{T}(undef, p.sz...), p, ah)
 *(p::B200Plan{T,:c2c}, a::B200Array{Complex{T}}) where T = mul!(similar(a), p, a)
 \(p::B200Plan{T,:c2c}, a::B200Array{Complex{T}}) where T = ldiv!(similar(a), p, a)
+# `fft / ifft / rfft / irfft` (FFTW names re-exported by the reference, src/FourierFlows.jl:72; `jacobianh` of user code calls them)
+FourierFlows.rfft(a::B200Array{T}) where T<:AbstractFloat = plan_flows_rfft(a) * a
+FourierFlows.irfft(ah::B200Array{Complex{T}}, nx::Integer) where T = makeplan(T, (Int(nx), size(ah)[2:end]...), :r2c) \ ah
+FourierFlows.fft(a::B200Array{Complex{T}}) where T = plan_flows_fft(a) * a
+FourierFlows.ifft(a::B200Array{Complex{T}}) where T = plan_flows_fft(a) \ a
 
 # ---------------------------------------------------------------- descriptors shared by the grid-side kernels
 struct FFBDesc

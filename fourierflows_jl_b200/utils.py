@@ -6,8 +6,10 @@ from __future__ import annotations
 
 import ctypes as C
 
+import numpy as np
+
 from . import _lib as L
-from .array import DevArray, ffb_dtype
+from .array import DevArray, cxtype, ffb_dtype, fltype
 
 
 def axpby(out: DevArray, a, x: DevArray, b=0.0, y: DevArray = None):
@@ -101,3 +103,50 @@ def jacobian(a: DevArray, b: DevArray, grid):
     """`jacobian(a, b, grid)` (src/utils.jl:212-218)."""
     jh = jacobianh(a, b, grid)
     return (grid.rfftplan if a.dtype.kind != "c" else grid.fftplan).solve(jh)
+
+
+# ---------------------------------------------------------------- `fft / ifft / rfft / irfft` (re-exported FFTW names, src/FourierFlows.jl:72)
+# Allocating whole-array transforms; the plan of a (shape, type, kind) is kept for the next call (a few, least recently used dropped:
+# a plan owns twiddle tables and scratch).
+_FREE_PLANS: dict = {}
+_FREE_PLANS_MAX = 4
+
+
+def _free_plan(shape, T, kind):
+    from .domains import Plan
+    key = (tuple(int(v) for v in shape), np.dtype(T).str, int(kind))
+    plan = _FREE_PLANS.pop(key, None)
+    if plan is None:
+        plan = Plan(key[0], T, kind)
+    _FREE_PLANS[key] = plan                     # most recently used last
+    while len(_FREE_PLANS) > _FREE_PLANS_MAX:
+        _FREE_PLANS.pop(next(iter(_FREE_PLANS)))
+    return plan
+
+
+def rfft(a: DevArray) -> DevArray:
+    """`rfft(a)`: real (nx, ny, nz) -> complex (nx/2+1, ny, nz), unnormalised, all dimensions"""
+    if np.dtype(a.dtype).kind != "f":
+        raise TypeError("rfft needs a real array")
+    return _free_plan(a.shape, a.dtype, L.FFB_R2C) * a
+
+
+def irfft(ah: DevArray, nx: int) -> DevArray:
+    """`irfft(ah, nx)`: complex (nx/2+1, ny, nz) -> real (nx, ny, nz), scaled by 1/(nx*ny*nz); `nx` = first physical dimension"""
+    if np.dtype(ah.dtype).kind != "c" or ah.shape[0] != int(nx) // 2 + 1:
+        raise ValueError("irfft(ah, nx): ah must be complex with size(ah, 1) == nx/2 + 1")
+    return _free_plan((int(nx),) + tuple(ah.shape[1:]), fltype(ah.dtype), L.FFB_R2C).solve(ah)
+
+
+def fft(a: DevArray) -> DevArray:
+    """`fft(a)` of a complex array, all dimensions, unnormalised"""
+    if np.dtype(a.dtype).kind != "c":
+        raise TypeError("fft needs a complex array (convert a real field first, or use rfft)")
+    return _free_plan(a.shape, fltype(a.dtype), L.FFB_C2C) * a
+
+
+def ifft(ah: DevArray) -> DevArray:
+    """`ifft(ah)` of a complex array, all dimensions, scaled by 1/N"""
+    if np.dtype(ah.dtype).kind != "c":
+        raise TypeError("ifft needs a complex array")
+    return _free_plan(ah.shape, fltype(ah.dtype), L.FFB_C2C).solve(ah)

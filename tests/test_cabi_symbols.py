@@ -96,3 +96,22 @@ def test_new_entry_points_validate_arguments_without_a_device(lib):
     if not ff.have_device():
         with pytest.raises(ff.FFBError):
             ff.PinnedBuffer((16,), "float64")
+
+
+def test_free_fft_functions_check_their_arguments_on_the_host():
+    """`rfft / irfft / fft / ifft` (src/FourierFlows.jl:72): type and shape errors are raised before any plan is created; without a
+    device the transform itself fails loudly (no NumPy fallback)."""
+    import numpy as np
+    import fourierflows_jl_b200 as ff
+
+    class Shaped:   # only shape / dtype are looked at before the plan is created
+        def __init__(self, shape, dtype):
+            self.shape, self.dtype = shape, np.dtype(dtype)
+    for fn, arg in ((ff.rfft, Shaped((8, 8), np.complex128)), (ff.fft, Shaped((8, 8), np.float64)), (ff.ifft, Shaped((8,), np.float32))):
+        with pytest.raises(TypeError):
+            fn(arg)
+    with pytest.raises(ValueError):
+        ff.irfft(Shaped((5, 8), np.complex128), 16)
+    if not ff.have_device():
+        with pytest.raises(ff.FFBError):
+            ff.rfft(Shaped((8, 8), np.float64))

@@ -330,3 +330,27 @@ def test_fused_l2_four_step_matches_two_kernel_form_and_oracle(ff, shape, T, tol
     dz = dev(ff, z)
     cplan.mul(dz, dz)
     assert relerr(dz.to_numpy(), np.fft.fftn(z.astype(np.complex128))) <= tol
+
+
+@pytest.mark.parametrize("T,tol", [(np.float64, 1e-12), (np.float32, 1e-5)], ids=["f64", "f32"])
+def test_free_fft_functions(ff, T, tol):
+    """`fft / ifft / rfft / irfft` (FFTW names re-exported by the reference, src/FourierFlows.jl:72) as allocating whole-array
+    transforms; plans are cached per (shape, type, kind) and the least recently used one is dropped."""
+    rng = np.random.default_rng(12)
+    cT = np.complex64 if T == np.float32 else np.complex128
+    for shape in ((30,), (64,), (16, 30), (128, 64), (8, 8, 8), (32, 30, 16)):      # six shapes: more than the cache holds
+        x = np.asfortranarray(rng.standard_normal(shape).astype(T))
+        xh = ff.rfft(dev(ff, x))
+        assert xh.shape == (shape[0] // 2 + 1,) + shape[1:] and xh.dtype == cT
+        assert relerr(xh.to_numpy(), fo.RfftPlan(shape, T) * x.astype(np.float64)) <= tol
+        assert relerr(ff.irfft(xh, shape[0]).to_numpy(), x) <= tol
+        z = np.asfortranarray((rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).astype(cT))
+        zh = ff.fft(dev(ff, z))
+        assert relerr(zh.to_numpy(), np.fft.fftn(z.astype(np.complex128))) <= tol
+        assert relerr(ff.ifft(zh).to_numpy(), z) <= tol
+    from fourierflows_jl_b200 import utils
+    assert len(utils._FREE_PLANS) <= utils._FREE_PLANS_MAX
+    with pytest.raises(TypeError):
+        ff.rfft(dev(ff, z))
+    with pytest.raises(ValueError):
+        ff.irfft(xh, 2 * shape[0])
